@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# Build the UNMODIFIED reference (CompressAI 1.2.0.dev0) into oracle/_ref/ so that tests and
+# bench.py --impl reference can run the reference's own CPU implementation of the hot path.
+# Recipe: SURVEY.md §8(c). Outputs go ONLY to oracle/_ref/ (git-ignored, travels with gpurun).
+# The reference's own build system is not run: two g++ lines on its source files where they lie.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${CAI_REFERENCE_ROOT:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/compressai" ]; then
+  echo "build_ref: $REF not present; keeping any prebuilt $OUT" >&2
+  exit 0
+fi
+PY="${PYTHON:-python}"
+INC_PY="$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])')"
+INC_PB="$($PY -c 'import pybind11;print(pybind11.get_include())')"
+SUF="$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')"
+rm -rf "$OUT"
+mkdir -p "$OUT"
+# "install" of the pure-python package (what `pip install --target` would do)
+cp -r "$REF/compressai" "$OUT/compressai"
+rm -rf "$OUT/compressai/cpp_exts"
+find "$OUT" -name '__pycache__' -type d -prune -exec rm -rf {} +
+printf '__version__ = "1.2.0.dev0"\n' > "$OUT/compressai/version.py"
+CXXFLAGS="-O3 -DNDEBUG -std=c++17 -shared -fPIC -fvisibility=hidden"
+g++ $CXXFLAGS -I"$INC_PY" -I"$INC_PB" -I"$REF/third_party/ryg_rans" -I"$REF/compressai/cpp_exts/rans" \
+    "$REF/compressai/cpp_exts/rans/rans_interface.cpp" -o "$OUT/compressai/ans$SUF"
+g++ $CXXFLAGS -I"$INC_PY" -I"$INC_PB" \
+    "$REF/compressai/cpp_exts/ops/ops.cpp" -o "$OUT/compressai/_CXX$SUF"
+echo "build_ref: reference installed in $OUT"
