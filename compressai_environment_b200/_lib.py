@@ -1,0 +1,106 @@
+"""ctypes binding of ``libcai_b200.so`` (C ABI declared in ``include/cai_b200.h``).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C compressai_environment_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcai_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+CAI_LAYOUT_NCHW = 0
+CAI_LAYOUT_NHWC = 1
+
+STATUS_TEXT = {
+    0: "ok",
+    1: "encoder slot overflow",
+    2: "cdf index out of range",
+    3: "Invalid `pmf`, non-finite or negative element found",
+    4: "Invalid `pmf`: at least one element must have a non-zero probability.",
+    5: "Invalid `pmf`: no symbol to steal frequency from",
+    6: "decoder ran past the end of the string",
+}
+
+# name -> (restype, argtypes).  Must list every symbol declared in include/cai_b200.h
+# (tests/test_abi.py cross-checks this table against the header and the built library).
+SIGNATURES = {
+    "cai_abi_version": (c_int, []),
+    "cai_last_error": (c_char_p, []),
+    "cai_device_info": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "cai_table_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p)]),
+    "cai_table_destroy": (None, [c_void_p]),
+    "cai_table_info": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]),
+    "cai_rans_slot_words": (c_int64, [c_int64]),
+    "cai_rans_encode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_void_p]),
+    "cai_rans_compact": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cai_rans_decode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                      c_void_p, c_int32, c_void_p, c_void_p]),
+    "cai_gc_quantize_index": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_int64,
+                                      c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cai_eb_quantize_index": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                      c_void_p]),
+    "cai_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "cai_pmf_to_quantized_cdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                         c_void_p]),
+}
+
+_lib = None
+
+
+class CaiError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libcai_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", CSRC_DIR, "-j8"], stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CaiError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header / library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if L.cai_abi_version() != 1:
+            raise CaiError("libcai_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().cai_last_error().decode("utf-8", "replace")
+        raise CaiError(f"{what or 'libcai_b200'} failed (rc={rc}): {msg}")
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise CaiError(f"{name} must live on a CUDA device (got {t.device}); there is no CPU fallback")
+    return t
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

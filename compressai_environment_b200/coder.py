@@ -1,0 +1,163 @@
+"""Tensor-level front end of the batched rANS coder (``cai_rans_*`` / ``cai_table_*`` in the C ABI).
+
+Host mirror of what ``EntropyModel.compress`` / ``decompress`` do around the coder in the reference
+(compressai/entropy_models/entropy_models.py:259-267, :313-323) -- minus the per-image Python loop and
+the five ``.tolist()`` round trips: all strings of a batch are coded by one kernel launch and the byte
+strings come back in a single device-to-host copy.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, lib, ptr, require_cuda
+
+
+class CdfTable:
+    """Packed CDF tables resident in HBM (``cai_table_t``).  Built once per ``update()``."""
+
+    def __init__(self, quantized_cdf: torch.Tensor, cdf_length: torch.Tensor, offset: torch.Tensor):
+        require_cuda(quantized_cdf, "_quantized_cdf")
+        if quantized_cdf.dim() != 2:
+            raise ValueError(f"Invalid CDF size {tuple(quantized_cdf.size())}")
+        cdf = quantized_cdf.detach().to(torch.int32).contiguous()
+        ln = cdf_length.detach().reshape(-1).to(device=cdf.device, dtype=torch.int32).contiguous()
+        off = offset.detach().reshape(-1).to(device=cdf.device, dtype=torch.int32).contiguous()
+        if ln.numel() != cdf.size(0) or off.numel() != cdf.size(0):
+            raise ValueError("cdf, cdf_length and offset disagree on the number of rows")
+        self.device = cdf.device
+        self.K, self.Lmax = int(cdf.size(0)), int(cdf.size(1))
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().cai_table_create(ptr(cdf), ptr(ln), ptr(off), self.K, self.Lmax, current_stream(),
+                                         ctypes.byref(self._h)), "cai_table_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        K, nb, inl = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        by = ctypes.c_int64()
+        check(lib().cai_table_info(self._h, ctypes.byref(K), ctypes.byref(by), ctypes.byref(nb), ctypes.byref(inl)))
+        return {"K": K.value, "blob_bytes": by.value, "lut_buckets": nb.value, "in_smem": bool(inl.value)}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().cai_table_destroy(h)
+            except Exception:
+                pass
+
+
+def slot_words(n: int) -> int:
+    return int(lib().cai_rans_slot_words(int(n)))
+
+
+def _raise_status(status: torch.Tensor, what: str):
+    st = status.cpu()
+    bad = torch.nonzero(st != 0).reshape(-1)
+    hard = [int(i) for i in bad if int(st[i]) != 6]
+    if hard:
+        i = hard[0]
+        raise ValueError(f"{what}: string {i}: {_lib.STATUS_TEXT.get(int(st[i]), int(st[i]))}")
+
+
+class EncodedBatch:
+    """Device-side result of one encode launch (slots + lengths); ``to_bytes()`` brings strings to host."""
+
+    def __init__(self, slots, n_words, status, slot_w):
+        self.slots, self.n_words, self.status, self.slot_w = slots, n_words, status, slot_w
+
+    def to_bytes(self) -> List[bytes]:
+        B = self.n_words.numel()
+        if B == 0:
+            return []
+        dev = self.slots.device
+        nw = self.n_words.cpu()  # sync point: sizes are needed to allocate the packed buffer
+        _raise_status(self.status, "rANS encode")
+        total = int(nw.sum())
+        begin = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        packed = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().cai_rans_compact(ptr(self.slots), self.slot_w, ptr(self.n_words), B, ptr(begin), ptr(packed),
+                                         total, current_stream()), "cai_rans_compact")
+        host = torch.empty(max(total, 1), dtype=torch.int32, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        raw = host.numpy().view(np.uint8)
+        ends = np.cumsum(nw.numpy().astype(np.int64)) * 4
+        out, a = [], 0
+        for e in ends:
+            out.append(raw[a:e].tobytes())
+            a = int(e)
+        return out
+
+
+def encode(table: CdfTable, symbols: torch.Tensor, indexes: torch.Tensor) -> EncodedBatch:
+    """Encode B equal-length strings.  ``symbols`` / ``indexes``: int32 [B, n] in coder order."""
+    require_cuda(symbols, "symbols")
+    require_cuda(indexes, "indexes")
+    assert symbols.dtype == torch.int32 and indexes.dtype == torch.int32
+    assert symbols.is_contiguous() and indexes.is_contiguous() and symbols.shape == indexes.shape
+    B = int(symbols.size(0)) if symbols.dim() > 0 else 0
+    n = int(symbols.numel() // B) if B else 0
+    dev = symbols.device
+    sw = slot_words(n)
+    slots = torch.empty((max(B, 1), sw), dtype=torch.int32, device=dev)
+    n_words = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().cai_rans_encode_batch(table.handle, ptr(symbols), ptr(indexes), None, n, B, ptr(slots), sw,
+                                          ptr(n_words), ptr(status), current_stream()), "cai_rans_encode_batch")
+    return EncodedBatch(slots, n_words, status, sw)
+
+
+def strings_to_device(strings: Sequence[bytes], device) -> tuple:
+    """Concatenate byte strings (zero padded to whole words) -> (uint32-as-int32 words, int64 begins)."""
+    lens = np.array([(len(s) + 3) // 4 for s in strings], dtype=np.int64)
+    begin = np.zeros(len(strings) + 1, dtype=np.int64)
+    np.cumsum(lens, out=begin[1:])
+    total = int(begin[-1])
+    host = torch.zeros(max(total, 1) * 4, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    hv = host.numpy()
+    for s, a in zip(strings, begin[:-1]):
+        hv[a * 4:a * 4 + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    words = host.view(torch.int32).to(device, non_blocking=True)
+    wb = torch.from_numpy(begin).to(device, non_blocking=True)
+    return words, wb, host
+
+
+def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, state: Optional[torch.Tensor] = None,
+           resume: bool = False, device_words=None) -> torch.Tensor:
+    """Decode B strings; ``indexes`` int32 [B, n] in coder order.  Returns int32 [B, n]."""
+    require_cuda(indexes, "indexes")
+    assert indexes.dtype == torch.int32 and indexes.is_contiguous()
+    B = int(indexes.size(0)) if indexes.dim() > 0 else 0
+    n = int(indexes.numel() // B) if B else 0
+    dev = indexes.device
+    out = torch.empty_like(indexes)
+    if B == 0:
+        return out
+    if device_words is None:
+        if len(strings) != B:
+            raise ValueError("Invalid strings or indexes parameters")
+        words, wb, keep = strings_to_device(strings, dev)
+    else:
+        words, wb = device_words
+        keep = None
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().cai_rans_decode_batch(table.handle, ptr(words), ptr(wb), ptr(indexes), None, n, B, ptr(out),
+                                          ptr(state), 1 if resume else 0, ptr(status), current_stream()),
+              "cai_rans_decode_batch")
+    if keep is not None:
+        # the pinned staging buffer must outlive the async H2D copy
+        torch.cuda.current_stream(dev).synchronize()
+        _raise_status(status, "rANS decode")
+    return out

@@ -1,0 +1,303 @@
+// quantize.cu -- fused quantise / index / dequantise kernels (HBM-bound, single pass).
+//
+// What they replace (reference tree, compressai/entropy_models/entropy_models.py):
+//   :155-180  EntropyModel.quantize(mode="symbols")   round-half-even(x - mean) -> int32
+//   :188-197  EntropyModel.dequantize                 float(sym) + mean
+//   :518-541  EntropyBottleneck._build_indexes / compress front end (channel index, medians)
+//   :684-689  GaussianConditional.build_indexes       63 sequential compare+subtract passes -> ONE pass
+//
+// Layout: inputs are logical (N, C, HW) latents stored NCHW or NHWC (channels-last, what the conv
+// kernels produce); integer outputs are always in coder order (N, C, HW) so that string b is a
+// contiguous run.  The NHWC variants transpose 32x32 tiles through shared memory so that both the
+// loads (along C) and the stores (along HW) are full 128-byte lines.
+//
+// Algorithmic bytes per element: GC 16 B (20 B with means), EB 12 B, dequantize 8-12 B.
+#include "common.cuh"
+
+namespace cai {
+
+constexpr int kTabRep = 32;       // scale table replicated per bank -> conflict-free binary search
+constexpr int kMaxRepT = 128;     // replicate when T <= 128 (16 KB); otherwise a single copy
+constexpr int kMaxT = 4096;
+
+struct ScaleTab {
+  const float *t;  // shared memory
+  int T;
+  int rep;  // 32 or 1
+  int lane;
+  // (T-1) - #{ j < T-1 : s <= t[j] }  ==  first j in [0, T-1) with s <= t[j], else T-1.  NaN -> T-1.
+  __device__ __forceinline__ int32_t index_of(float s, float bound) const {
+    s = (s < bound) ? bound : s;  // torch.max(x, bound): NaN propagates (LowerBound, bound_ops.py:36-37)
+    int lo = 0, hi = T - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s <= t[mid * rep + (rep == 1 ? 0 : lane)])
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    return lo;
+  }
+};
+
+__device__ __forceinline__ void load_table(float *s_tab, const float *__restrict__ table, int T, int rep) {
+  for (int i = threadIdx.x; i < T * rep; i += blockDim.x) s_tab[i] = table[i / rep];
+  __syncthreads();
+}
+
+__device__ __forceinline__ int32_t quant_sym(float y, float mean) {
+  // clone(); sub_(means); round(); .int()   (entropy_models.py:167-180).  rintf = round-half-even.
+  const float r = rintf(__fsub_rn(y, mean));
+  // float -> int32 as the x86 reference does (cvttss2si): out-of-range / NaN -> INT_MIN
+  if (!(r >= -2147483648.0f && r < 2147483648.0f)) return static_cast<int32_t>(0x80000000u);
+  return static_cast<int32_t>(r);
+}
+
+// ---- NCHW (pure elementwise, 4 elements per thread) ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+gc_qi_nchw_kernel(const float *__restrict__ y, const float *__restrict__ scales, const float *__restrict__ means,
+                  const float *__restrict__ table, int T, float bound, int64_t total, int vec,
+                  int32_t *__restrict__ sym, int32_t *__restrict__ idx) {
+  extern __shared__ float s_tab[];
+  const int rep = (T <= kMaxRepT) ? kTabRep : 1;
+  if (scales) load_table(s_tab, table, T, rep);
+  ScaleTab st{s_tab, T, rep, static_cast<int>(threadIdx.x & 31)};
+  const int64_t nvec = vec ? (total >> 2) : 0;  // vector path needs 16-byte aligned bases
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    if (y) {
+      const float4 a = __ldcs(reinterpret_cast<const float4 *>(y) + v);
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (means) m = __ldcs(reinterpret_cast<const float4 *>(means) + v);
+      int4 o;
+      o.x = quant_sym(a.x, m.x);
+      o.y = quant_sym(a.y, m.y);
+      o.z = quant_sym(a.z, m.z);
+      o.w = quant_sym(a.w, m.w);
+      reinterpret_cast<int4 *>(sym)[v] = o;
+    }
+    if (scales) {
+      const float4 s = __ldcs(reinterpret_cast<const float4 *>(scales) + v);
+      int4 o;
+      o.x = st.index_of(s.x, bound);
+      o.y = st.index_of(s.y, bound);
+      o.z = st.index_of(s.z, bound);
+      o.w = st.index_of(s.w, bound);
+      reinterpret_cast<int4 *>(idx)[v] = o;
+    }
+  }
+  // tail (total % 4)
+  const int64_t t0 = nvec << 2;
+  for (int64_t i = t0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    if (y) sym[i] = quant_sym(y[i], means ? means[i] : 0.f);
+    if (scales) idx[i] = st.index_of(scales[i], bound);
+  }
+}
+
+// ---- NHWC -> coder order (32x32 tile transpose) --------------------------------------------------------
+// grid: x = hw tiles, y = c tiles, z = n ; block (32, 8)
+__global__ void __launch_bounds__(256)
+gc_qi_nhwc_kernel(const float *__restrict__ y, const float *__restrict__ scales, const float *__restrict__ means,
+                  const float *__restrict__ table, int T, float bound, int64_t C, int64_t HW,
+                  int32_t *__restrict__ sym, int32_t *__restrict__ idx) {
+  extern __shared__ float s_tab[];
+  __shared__ int32_t t_sym[32][33];
+  __shared__ int32_t t_idx[32][33];
+  const int rep = (T <= kMaxRepT) ? kTabRep : 1;
+  if (scales) load_table(s_tab, table, T, rep);
+  ScaleTab st{s_tab, T, rep, static_cast<int>(threadIdx.x)};
+  const int64_t n = blockIdx.z;
+  const int64_t hw0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t hw = hw0 + ty + 8 * r, c = c0 + tx;
+    if (hw < HW && c < C) {
+      const int64_t i = (n * HW + hw) * C + c;
+      if (y) t_sym[ty + 8 * r][tx] = quant_sym(__ldcs(y + i), means ? __ldcs(means + i) : 0.f);
+      if (scales) t_idx[ty + 8 * r][tx] = st.index_of(__ldcs(scales + i), bound);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t c = c0 + ty + 8 * r, hw = hw0 + tx;
+    if (hw < HW && c < C) {
+      const int64_t o = (n * C + c) * HW + hw;
+      if (y) sym[o] = t_sym[tx][ty + 8 * r];
+      if (scales) idx[o] = t_idx[tx][ty + 8 * r];
+    }
+  }
+}
+
+// ---- entropy bottleneck front end ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eb_qi_nchw_kernel(const float *__restrict__ x, const float *__restrict__ medians, int64_t C, int64_t HW,
+                  int64_t total, int32_t *__restrict__ sym, int32_t *__restrict__ idx) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int32_t c = static_cast<int32_t>((i / HW) % C);
+    if (sym) sym[i] = quant_sym(__ldcs(x + i), __ldg(medians + c));
+    if (idx) idx[i] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+eb_qi_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ medians, int64_t C, int64_t HW,
+                  int32_t *__restrict__ sym, int32_t *__restrict__ idx) {
+  __shared__ int32_t t_sym[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t hw0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (sym) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t hw = hw0 + ty + 8 * r, c = c0 + tx;
+      if (hw < HW && c < C) t_sym[ty + 8 * r][tx] = quant_sym(__ldcs(x + (n * HW + hw) * C + c), __ldg(medians + c));
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t c = c0 + ty + 8 * r, hw = hw0 + tx;
+    if (hw < HW && c < C) {
+      const int64_t o = (n * C + c) * HW + hw;
+      if (sym) sym[o] = t_sym[tx][ty + 8 * r];
+      if (idx) idx[o] = static_cast<int32_t>(c);
+    }
+  }
+}
+
+// ---- dequantise ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+deq_nchw_kernel(const int32_t *__restrict__ sym, const float *__restrict__ means, const float *__restrict__ medians,
+                int64_t C, int64_t HW, int64_t total, float *__restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float v = static_cast<float>(__ldcs(sym + i));
+    if (means) v = __fadd_rn(v, __ldcs(means + i));
+    if (medians) v = __fadd_rn(v, __ldg(medians + (i / HW) % C));
+    out[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+deq_nhwc_kernel(const int32_t *__restrict__ sym, const float *__restrict__ means, const float *__restrict__ medians,
+                int64_t C, int64_t HW, float *__restrict__ out) {
+  __shared__ int32_t t_sym[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t hw0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t c = c0 + ty + 8 * r, hw = hw0 + tx;
+    if (hw < HW && c < C) t_sym[ty + 8 * r][tx] = __ldcs(sym + (n * C + c) * HW + hw);  // [c_local][hw_local]
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t hw = hw0 + ty + 8 * r, c = c0 + tx;
+    if (hw < HW && c < C) {
+      const int64_t o = (n * HW + hw) * C + c;
+      float v = static_cast<float>(t_sym[tx][ty + 8 * r]);
+      if (means) v = __fadd_rn(v, __ldcs(means + o));
+      if (medians) v = __fadd_rn(v, __ldg(medians + c));
+      out[o] = v;
+    }
+  }
+}
+
+static int elementwise_grid(const DeviceProps &dp, int64_t work_items, int threads) {
+  int64_t g = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(dp.sm_count) * 16;  // multiple of the SM count, grid-stride beyond
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace cai
+
+using namespace cai;
+
+extern "C" {
+
+int cai_gc_quantize_index(const float *y, const float *scales, const float *means, const float *scale_table,
+                          int32_t T, float scale_bound, int32_t layout, int64_t N, int64_t C, int64_t HW,
+                          int32_t *sym, int32_t *idx, cai_stream_t stream_) {
+  CAI_CHECK_ARG(N >= 0 && C >= 0 && HW >= 0, "cai_gc_quantize_index: negative size");
+  CAI_CHECK_ARG(layout == CAI_LAYOUT_NCHW || layout == CAI_LAYOUT_NHWC, "cai_gc_quantize_index: bad layout");
+  CAI_CHECK_ARG(!y || sym, "cai_gc_quantize_index: y given without sym output");
+  CAI_CHECK_ARG(!scales || (idx && scale_table && T >= 1 && T <= kMaxT),
+                "cai_gc_quantize_index: scales need idx, scale_table and 1 <= T <= %d", kMaxT);
+  CAI_CHECK_ARG(!means || y, "cai_gc_quantize_index: means given without y");
+  const int64_t total = N * C * HW;
+  if (total == 0 || (!y && !scales)) return CAI_OK;
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int rep = (T <= kMaxRepT) ? kTabRep : 1;
+  const size_t smem = scales ? sizeof(float) * static_cast<size_t>(T) * rep : 0;
+  if (layout == CAI_LAYOUT_NCHW || C == 1 || HW == 1) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(scales) |
+                           reinterpret_cast<uintptr_t>(means) | reinterpret_cast<uintptr_t>(sym) |
+                           reinterpret_cast<uintptr_t>(idx)) & 15u) == 0;
+    const int grid = elementwise_grid(dp, aligned ? (total + 3) / 4 : total, 256);
+    gc_qi_nchw_kernel<<<grid, 256, smem, stream>>>(y, scales, means, scale_table, T, scale_bound, total,
+                                                   aligned ? 1 : 0, sym, idx);
+  } else {
+    CAI_CHECK_ARG(N <= 65535 && (C + 31) / 32 <= 65535, "cai_gc_quantize_index: N or C too large for the grid");
+    dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(N));
+    gc_qi_nhwc_kernel<<<grid, dim3(32, 8), smem, stream>>>(y, scales, means, scale_table, T, scale_bound, C, HW, sym,
+                                                           idx);
+  }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_eb_quantize_index(const float *x, const float *medians, int32_t layout, int64_t N, int64_t C, int64_t HW,
+                          int32_t *sym, int32_t *idx, cai_stream_t stream_) {
+  CAI_CHECK_ARG(N >= 0 && C >= 0 && HW >= 0, "cai_eb_quantize_index: negative size");
+  CAI_CHECK_ARG(layout == CAI_LAYOUT_NCHW || layout == CAI_LAYOUT_NHWC, "cai_eb_quantize_index: bad layout");
+  CAI_CHECK_ARG(!sym || (x && medians), "cai_eb_quantize_index: sym needs x and medians");
+  const int64_t total = N * C * HW;
+  if (total == 0 || (!sym && !idx)) return CAI_OK;
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (layout == CAI_LAYOUT_NCHW || C == 1 || HW == 1) {
+    eb_qi_nchw_kernel<<<elementwise_grid(dp, total, 256), 256, 0, stream>>>(x, medians, C, HW, total, sym, idx);
+  } else {
+    CAI_CHECK_ARG(N <= 65535 && (C + 31) / 32 <= 65535, "cai_eb_quantize_index: N or C too large for the grid");
+    dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(N));
+    eb_qi_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, medians, C, HW, sym, idx);
+  }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_dequantize(const int32_t *sym, const float *means, const float *medians, int32_t layout, int64_t N,
+                   int64_t C, int64_t HW, float *out, cai_stream_t stream_) {
+  CAI_CHECK_ARG(N >= 0 && C >= 0 && HW >= 0, "cai_dequantize: negative size");
+  CAI_CHECK_ARG(layout == CAI_LAYOUT_NCHW || layout == CAI_LAYOUT_NHWC, "cai_dequantize: bad layout");
+  CAI_CHECK_ARG(!(means && medians), "cai_dequantize: give means or medians, not both");
+  const int64_t total = N * C * HW;
+  if (total == 0) return CAI_OK;
+  CAI_CHECK_ARG(sym && out, "cai_dequantize: NULL pointer");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (layout == CAI_LAYOUT_NCHW || C == 1 || HW == 1) {
+    deq_nchw_kernel<<<elementwise_grid(dp, total, 256), 256, 0, stream>>>(sym, means, medians, C, HW, total, out);
+  } else {
+    CAI_CHECK_ARG(N <= 65535 && (C + 31) / 32 <= 65535, "cai_dequantize: N or C too large for the grid");
+    dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(N));
+    deq_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(sym, means, medians, C, HW, out);
+  }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,625 @@
+// rans.cu -- batched, bit-exact Rans64 coder for sm_100a.
+//
+// What it replaces (reference tree):
+//   compressai/cpp_exts/rans/rans_interface.cpp:108-213  BufferedRansEncoder / RansEncoder
+//   compressai/cpp_exts/rans/rans_interface.cpp:215-359  RansDecoder (stateless and streaming)
+//   third_party/ryg_rans/rans64.h:59-142                 state machine
+//
+// Design.  One rANS stream is a strict serial chain (state_i depends on state_{i+1}), so the only
+// parallelism is across strings: ONE WARP PER STRING, thousands of strings per launch.  Inside a warp
+//   * the 32 lanes cooperate on everything that is NOT the chain: coalesced loads of symbols / indexes,
+//     CDF lookups in the shared-memory table (staged with one TMA bulk copy per CTA), escape
+//     expansion, exact reciprocals for the encoder's division -- one symbol per lane, software
+//     pipelined two chunks ahead of the chain;
+//   * the chain itself runs warp-uniformly over a 32-entry parameter buffer in shared memory (one
+//     LDS.128 broadcast per symbol), so its per-symbol latency is: renorm test, one 64x64 high
+//     multiply, one shift, one multiply-add (encoder) / one LUT hit, one multiply-add (decoder);
+//   * output words / symbols are collected one per lane and written as full 128-byte lines.
+//
+// Exact division.  Rans64EncPut needs q = x / freq, r = x % freq with x < 2^63, freq < 2^16
+// (rans64.h:92).  For freq >= 2 let l = ceil(log2 freq), m = ceil(2^(63+l) / freq) (fits 64 bits);
+// then q = umul64hi(x, m) >> (l-1) for every x < 2^63 (round-up reciprocal: the error term
+// e = m*freq - 2^(63+l) < freq <= 2^l, so x*e < 2^(63+l)).  The new state is
+//   ((x/f) << 16) + x%f + start = x + start + q * (2^16 - f).
+// freq == 1 uses m = 2^64-1, shift 0 (q = x - 1) and folds the missing 2^16 - 1 into the bias.
+// The 65536-entry table of m lives in HBM/L2 and is gathered one chunk ahead of the chain.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cai {
+
+constexpr int kMaxWarpsPerCta = 32;
+constexpr uint32_t kRansL_hi = 0u;  // documentation only: L = 2^31
+
+__device__ uint64_t g_rcp[65536];
+
+// host: exact reciprocal table
+static void build_rcp_host(uint64_t *tab) {
+  tab[0] = 0;
+  tab[1] = ~0ull;
+  for (uint32_t f = 2; f < 65536; ++f) {
+    uint32_t l = 0;
+    while ((1u << l) < f) ++l;
+    const unsigned __int128 num = (static_cast<unsigned __int128>(1) << (63 + l)) + (f - 1);
+    tab[f] = static_cast<uint64_t>(num / f);
+  }
+}
+
+static int ensure_rcp_table(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64) return CAI_E_NO_DEVICE;
+  if (done[device]) return CAI_OK;
+  static uint64_t *host = nullptr;
+  if (!host) {
+    host = new uint64_t[65536];
+    build_rcp_host(host);
+  }
+  CAI_CUDA(cudaMemcpyToSymbol(g_rcp, host, sizeof(uint64_t) * 65536));
+  done[device] = true;
+  return CAI_OK;
+}
+
+// ---- shared-memory carve-up ---------------------------------------------------------------------------
+// dynamic smem: [ blob (table) | per-warp staging ]
+struct __align__(16) EncParam {
+  uint32_t m_lo;
+  uint32_t m_hi;        // bit 31 (bit 63 of m, always 1 in the true value) carries the escape flag inverted: see pack
+  uint32_t bias_shift;  // bias (17 bits) | shift << 20
+  uint32_t thr;         // freq << 15 : renormalise iff (x >> 32) >= thr
+};
+struct __align__(16) DecParam {
+  uint32_t cdf_off;
+  int32_t maxv;
+  int32_t offset;
+  uint32_t lut_off;
+};
+
+constexpr int kEncWarpBytes = 2 * 32 * (sizeof(EncParam) + sizeof(uint32_t));  // 1280
+constexpr int kDecWarpBytes = 2 * 32 * sizeof(DecParam);                       // 1024
+
+template <bool kSmem>
+struct TableView {
+  const RowMeta *meta;
+  const uint16_t *cdf;
+  const uint2 *lut;
+  int32_t K;
+  int32_t lut_shift;
+};
+
+// ---- encoder -------------------------------------------------------------------------------------------
+struct EncEmit {
+  uint32_t *slot_end;  // one past the last word of this string's slot
+  int64_t cap;
+  int64_t cnt;
+  uint32_t buf;
+  int lane;
+  __device__ __forceinline__ void push(uint32_t w) {
+    if ((static_cast<int>(cnt) & 31) == lane) buf = w;
+    cnt += 1;
+    if ((cnt & 31) == 0) {
+      const int64_t k = cnt - 32 + lane;
+      if (k < cap) slot_end[-1 - k] = buf;
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    const int rem = static_cast<int>(cnt & 31);
+    if (lane < rem) {
+      const int64_t k = (cnt - rem) + lane;
+      if (k < cap) slot_end[-1 - k] = buf;
+    }
+  }
+};
+
+template <bool kSmem>
+__global__ void __launch_bounds__(1024, 1)
+rans_encode_kernel(const unsigned char *__restrict__ blob, uint32_t enc_bytes, const int32_t *__restrict__ symbols,
+                   const int32_t *__restrict__ indexes, const int64_t *__restrict__ str_begin,
+                   int64_t n_per_string, int32_t B, uint32_t *__restrict__ slots, int64_t slot_words,
+                   int32_t *__restrict__ n_words, int32_t *__restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bar;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+
+  const unsigned char *tbl = blob;
+  uint32_t stage_off = 0;
+  if (kSmem) {
+    stage_blob(smem, blob, enc_bytes, &s_bar);
+    tbl = smem;
+    stage_off = (enc_bytes + 127u) & ~127u;
+  }
+  const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(tbl);
+  const int32_t K = hdr->K;
+  const uint4 *meta = reinterpret_cast<const uint4 *>(tbl + hdr->off_meta);
+  const uint16_t *cdf16 = reinterpret_cast<const uint16_t *>(tbl + hdr->off_cdf);
+
+  EncParam *pbuf = reinterpret_cast<EncParam *>(smem + stage_off + warp * kEncWarpBytes);
+  uint32_t *rbuf = reinterpret_cast<uint32_t *>(pbuf + 64);
+
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * warps + warp; b < B;
+       b += static_cast<int64_t>(gridDim.x) * warps) {
+    const int64_t beg = str_begin ? str_begin[b] : b * n_per_string;
+    const int64_t n = str_begin ? (str_begin[b + 1] - beg) : n_per_string;
+    const int32_t *sym = symbols + beg;
+    const int32_t *idx = indexes + beg;
+    int32_t st = CAI_S_OK;
+
+    EncEmit em;
+    em.slot_end = slots + (b + 1) * slot_words;
+    em.cap = slot_words;
+    em.cnt = 0;
+    em.buf = 0;
+    em.lane = lane;
+
+    uint64_t x = 1ull << 31;
+    const int64_t nchunks = (n + 31) >> 5;
+
+    // pipeline registers
+    int32_t r_sym = 0, r_idx = 0;                          // stage 1: raw loads for chunk j-1
+    uint32_t p_bias_shift = 0, p_thr = 0, p_raw = 0;       // stage 2: lookups for chunk j
+    uint32_t p_freq = 1, p_esc = 0;
+
+    auto stage1 = [&](int64_t j) {
+      const int64_t i = (j << 5) + lane;
+      if (i < n) {
+        r_sym = __ldg(sym + i);
+        r_idx = __ldg(idx + i);
+      } else {
+        r_sym = 0;
+        r_idx = 0;
+      }
+    };
+    auto stage2 = [&](int64_t j) {
+      const int64_t i = (j << 5) + lane;
+      int32_t k = r_idx;
+      if (i < n && (k < 0 || k >= K)) {
+        st = CAI_S_BAD_INDEX;
+        k = 0;
+      }
+      const uint4 m = meta[k];  // cdf_off, len, offset, lut_off
+      const int32_t maxv = static_cast<int32_t>(m.y) - 2;
+      int32_t v = static_cast<int32_t>(static_cast<uint32_t>(r_sym) - m.z);
+      uint32_t raw = 0, esc = 0;
+      if (v < 0) {
+        raw = static_cast<uint32_t>(-2) * static_cast<uint32_t>(v) - 1u;
+        v = maxv;
+        esc = 1;
+      } else if (v >= maxv) {
+        raw = 2u * static_cast<uint32_t>(v - maxv);
+        v = maxv;
+        esc = 1;
+      }
+      if (maxv < 0) v = 0;  // malformed row: stay in bounds
+      const uint32_t c0 = cdf16[m.x + v];
+      const uint32_t c1 = cdf16[m.x + v + 1];
+      uint32_t freq = (c1 - c0) & 0xFFFFu;
+      if (freq == 0) freq = 1;  // malformed table: keep the chain well defined
+      uint32_t shift = 0, bias = c0;
+      if (freq == 1)
+        bias += 65535u;
+      else
+        shift = 31 - __clz(freq - 1);
+      p_bias_shift = bias | (shift << 20);
+      p_thr = freq << 15;
+      p_raw = raw;
+      p_esc = esc;
+      p_freq = freq;
+    };
+
+    if (nchunks > 0) {
+      stage1(nchunks - 1);
+      stage2(nchunks - 1);
+      if (nchunks > 1) stage1(nchunks - 2);
+    }
+    uint64_t p_m = __ldg(&g_rcp[p_freq]);
+
+    for (int64_t j = nchunks - 1; j >= 0; --j) {
+      const int bsel = static_cast<int>(j & 1);
+      EncParam *pp = pbuf + bsel * 32;
+      uint32_t *rr = rbuf + bsel * 32;
+      {
+        EncParam e;
+        e.m_lo = static_cast<uint32_t>(p_m);
+        // true m always has bit 63 set; store the escape flag there (1 = no escape keeps the bit)
+        e.m_hi = static_cast<uint32_t>(p_m >> 32) & (p_esc ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+        e.bias_shift = p_bias_shift;
+        e.thr = p_thr;
+        pp[lane] = e;
+        rr[lane] = p_raw;
+      }
+      __syncwarp();
+      if (j >= 1) {
+        stage2(j - 1);
+        p_m = __ldg(&g_rcp[p_freq]);
+        if (j >= 2) stage1(j - 2);
+      }
+      const int64_t rem = n - (j << 5);
+      const int nvalid = rem < 32 ? static_cast<int>(rem) : 32;
+#pragma unroll 4
+      for (int l = nvalid - 1; l >= 0; --l) {
+        const uint4 e = *reinterpret_cast<const uint4 *>(pp + l);
+        if (!(e.y & 0x80000000u)) {
+          // escape: payload nibbles MSB first, then the count nibble (we walk the entry list backwards)
+          const uint32_t raw = rr[l];
+          const int nb = raw ? ((35 - __clz(raw)) >> 2) : 0;
+          for (int t = nb - 1; t >= 0; --t) {
+            if (static_cast<uint32_t>(x >> 32) >= (1u << 27)) {  // x >= 2^59
+              em.push(static_cast<uint32_t>(x));
+              x >>= 32;
+            }
+            x = (x << 4) | ((raw >> (4 * t)) & 15u);
+          }
+          if (static_cast<uint32_t>(x >> 32) >= (1u << 27)) {
+            em.push(static_cast<uint32_t>(x));
+            x >>= 32;
+          }
+          x = (x << 4) | static_cast<uint32_t>(nb);
+        }
+        if (static_cast<uint32_t>(x >> 32) >= e.w) {
+          em.push(static_cast<uint32_t>(x));
+          x >>= 32;
+        }
+        const uint64_t m = (static_cast<uint64_t>(e.y | 0x80000000u) << 32) | e.x;
+        const uint32_t shift = e.z >> 20;
+        const uint32_t bias = e.z & 0xFFFFFu;
+        const uint32_t cmpl = 65536u - (e.w >> 15);
+        const uint64_t q = __umul64hi(x, m) >> shift;
+        x = x + bias + q * cmpl;
+      }
+    }
+    em.push(static_cast<uint32_t>(x >> 32));
+    em.push(static_cast<uint32_t>(x));
+    em.finish();
+    if (em.cnt > em.cap) st = CAI_S_OVERFLOW;
+    st = __reduce_max_sync(0xffffffffu, st);
+    if (lane == 0) {
+      n_words[b] = static_cast<int32_t>(em.cnt > em.cap ? em.cap : em.cnt);
+      if (status) status[b] = st;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- decoder -------------------------------------------------------------------------------------------
+struct WordFeed {
+  const uint32_t *w;
+  int64_t nw;
+  int64_t pos;    // next word to consume
+  int64_t cbase;  // multiple of 32: wcur holds [cbase, cbase+32)
+  uint32_t wcur, wnext, next;
+  int lane;
+  __device__ __forceinline__ uint32_t load(int64_t base) const {
+    const int64_t i = base + lane;
+    return (i >= 0 && i < nw) ? __ldg(w + i) : 0u;
+  }
+  __device__ __forceinline__ void init(int64_t p) {
+    pos = p;
+    cbase = p & ~static_cast<int64_t>(31);
+    wcur = load(cbase);
+    wnext = load(cbase + 32);
+    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31));
+  }
+  __device__ __forceinline__ uint32_t take() {
+    const uint32_t r = next;
+    pos += 1;
+    if ((pos & 31) == 0) {
+      wcur = wnext;
+      cbase += 32;
+      wnext = load(cbase + 32);
+    }
+    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31));
+    return r;
+  }
+};
+
+template <bool kSmem>
+__global__ void __launch_bounds__(1024, 1)
+rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, const uint32_t *__restrict__ words,
+                   const int64_t *__restrict__ word_begin, const int32_t *__restrict__ indexes,
+                   const int64_t *__restrict__ str_begin, int64_t n_per_string, int32_t B,
+                   int32_t *__restrict__ out, uint64_t *__restrict__ state, int32_t resume,
+                   int32_t *__restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bar;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+
+  const unsigned char *tbl = blob;
+  uint32_t stage_off = 0;
+  if (kSmem) {
+    stage_blob(smem, blob, blob_bytes, &s_bar);
+    tbl = smem;
+    stage_off = (blob_bytes + 127u) & ~127u;
+  }
+  const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(tbl);
+  const int32_t K = hdr->K;
+  const int lut_shift = hdr->lut_shift;
+  const uint4 *meta = reinterpret_cast<const uint4 *>(tbl + hdr->off_meta);
+  const uint16_t *cdf16 = reinterpret_cast<const uint16_t *>(tbl + hdr->off_cdf);
+  const uint2 *lut = reinterpret_cast<const uint2 *>(tbl + hdr->off_lut);
+
+  DecParam *pbuf = reinterpret_cast<DecParam *>(smem + stage_off + warp * kDecWarpBytes);
+
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * warps + warp; b < B;
+       b += static_cast<int64_t>(gridDim.x) * warps) {
+    const int64_t beg = str_begin ? str_begin[b] : b * n_per_string;
+    const int64_t n = str_begin ? (str_begin[b + 1] - beg) : n_per_string;
+    const int32_t *idx = indexes + beg;
+    int32_t *dst = out + beg;
+    int32_t st = CAI_S_OK;
+
+    WordFeed wf;
+    wf.w = words + word_begin[b];
+    wf.nw = word_begin[b + 1] - word_begin[b];
+    wf.lane = lane;
+    uint64_t x;
+    if (resume && state) {
+      x = state[2 * b];
+      wf.init(static_cast<int64_t>(state[2 * b + 1]));
+    } else {
+      wf.init(0);
+      const uint32_t lo = wf.take();
+      const uint32_t hi = wf.take();
+      x = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+    }
+
+    const int64_t nchunks = (n + 31) >> 5;
+    int32_t r_idx = 0;
+    auto stage1 = [&](int64_t j) {
+      const int64_t i = (j << 5) + lane;
+      r_idx = (i < n) ? __ldg(idx + i) : 0;
+    };
+    if (nchunks > 0) stage1(0);
+
+    for (int64_t j = 0; j < nchunks; ++j) {
+      DecParam *pp = pbuf + static_cast<int>(j & 1) * 32;
+      {
+        int32_t k = r_idx;
+        if (k < 0 || k >= K) {
+          if ((j << 5) + lane < n) st = CAI_S_BAD_INDEX;
+          k = 0;
+        }
+        const uint4 m = meta[k];
+        DecParam d;
+        d.cdf_off = m.x;
+        d.maxv = static_cast<int32_t>(m.y) - 2;
+        d.offset = static_cast<int32_t>(m.z);
+        d.lut_off = m.w;
+        pp[lane] = d;
+      }
+      __syncwarp();
+      if (j + 1 < nchunks) stage1(j + 1);
+      const int64_t rem = n - (j << 5);
+      const int nvalid = rem < 32 ? static_cast<int>(rem) : 32;
+      int32_t myout = 0;
+#pragma unroll 2
+      for (int l = 0; l < nvalid; ++l) {
+        const uint4 d = *reinterpret_cast<const uint4 *>(pp + l);
+        const int32_t maxv = static_cast<int32_t>(d.y);
+        const uint32_t cf = static_cast<uint32_t>(x) & 0xFFFFu;
+        const uint2 e = lut[d.w + (cf >> lut_shift)];
+        uint32_t start = e.x & 0xFFFFu;
+        uint32_t freq = e.x >> 16;
+        int32_t s = static_cast<int32_t>(e.y);
+        if (freq == 0) {
+          // bucket spans several symbols: warp-cooperative forward search from s
+          const int32_t last = maxv + 1;  // position of the terminal entry (acts as +infinity)
+          for (;;) {
+            const int32_t cand = s + lane;
+            const bool hit = (cand + 1 >= last) || (static_cast<uint32_t>(cdf16[d.x + cand + 1]) > cf);
+            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+            if (ball) {
+              s += __ffs(ball) - 1;
+              break;
+            }
+            s += 32;
+          }
+          if (s > maxv) s = maxv < 0 ? 0 : maxv;
+          start = cdf16[d.x + s];
+          freq = (static_cast<uint32_t>(cdf16[d.x + s + 1]) - start) & 0xFFFFu;
+        }
+        x = static_cast<uint64_t>(freq) * (x >> 16) + (cf - start);
+        if (x < (1ull << 31)) x = (x << 32) | wf.take();
+        int32_t v = s;
+        if (s == maxv) {
+          // bypass / escape decoding (rans_interface.cpp:256-278)
+          uint32_t t = static_cast<uint32_t>(x) & 15u;
+          x >>= 4;
+          if (x < (1ull << 31)) x = (x << 32) | wf.take();
+          int32_t nb = static_cast<int32_t>(t);
+          while (t == 15u) {
+            t = static_cast<uint32_t>(x) & 15u;
+            x >>= 4;
+            if (x < (1ull << 31)) x = (x << 32) | wf.take();
+            nb += static_cast<int32_t>(t);
+          }
+          uint32_t raw = 0;
+          for (int32_t q = 0; q < nb; ++q) {
+            const uint32_t nib = static_cast<uint32_t>(x) & 15u;
+            x >>= 4;
+            if (x < (1ull << 31)) x = (x << 32) | wf.take();
+            if (q < 8) raw |= nib << (4 * q);
+          }
+          const int32_t sraw = static_cast<int32_t>(raw);
+          v = sraw >> 1;
+          v = (sraw & 1) ? (-v - 1) : (v + maxv);
+        }
+        if (lane == l) myout = v + static_cast<int32_t>(d.z);
+      }
+      if (lane < nvalid) dst[(j << 5) + lane] = myout;
+    }
+    if (wf.pos > wf.nw) st = st ? st : CAI_S_TRUNCATED;
+    st = __reduce_max_sync(0xffffffffu, st);
+    if (lane == 0) {
+      if (state) {
+        state[2 * b] = x;
+        state[2 * b + 1] = static_cast<uint64_t>(wf.pos);
+      }
+      if (status) status[b] = st;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- compaction ----------------------------------------------------------------------------------------
+__global__ void scan_words_kernel(const int32_t *__restrict__ n_words, int32_t B, int64_t *__restrict__ out_begin) {
+  __shared__ int64_t s_scan[1024];
+  __shared__ int64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int32_t base = 0; base < B; base += blockDim.x) {
+    const int32_t k = base + threadIdx.x;
+    const int64_t n = (k < B) ? static_cast<int64_t>(n_words[k]) : 0;
+    s_scan[threadIdx.x] = n;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+      const int64_t v = threadIdx.x >= d ? s_scan[threadIdx.x - d] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (k < B) out_begin[k] = s_carry + s_scan[threadIdx.x] - n;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += s_scan[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_begin[B] = s_carry;
+}
+
+__global__ void compact_kernel(const uint32_t *__restrict__ slots, int64_t slot_words,
+                               const int32_t *__restrict__ n_words, int32_t B,
+                               const int64_t *__restrict__ out_begin, uint32_t *__restrict__ out,
+                               int64_t out_cap) {
+  for (int32_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t n = n_words[b];
+    const uint32_t *src = slots + (static_cast<int64_t>(b) + 1) * slot_words - n;
+    const int64_t o = out_begin[b];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+      if (o + i < out_cap) out[o + i] = src[i];
+  }
+}
+
+}  // namespace cai
+
+using namespace cai;
+
+extern "C" {
+
+int64_t cai_rans_slot_words(int64_t n_symbols) {
+  if (n_symbols < 0) n_symbols = 0;
+  // <= 16 + 4*9 = 52 bits per symbol, 31 bits of initial state, 2 flush words; rounded to 128-byte lines
+  const int64_t w = (52 * n_symbols + 31 + 31) / 32 + 2;
+  return (w + 31) & ~static_cast<int64_t>(31);
+}
+
+static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
+  int w = (B + dp.sm_count - 1) / dp.sm_count;
+  if (w < 1) w = 1;
+  if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+  int g = (B + w - 1) / w;
+  if (g > dp.sm_count) g = dp.sm_count;  // persistent: each warp strides over strings
+  if (g < 1) g = 1;
+  *warps = w;
+  *grid = g;
+  return 0;
+}
+
+int cai_rans_encode_batch(cai_table_t t, const int32_t *symbols, const int32_t *indexes,
+                          const int64_t *str_begin, int64_t n_per_string, int32_t B, uint32_t *slots,
+                          int64_t slot_words, int32_t *n_words, int32_t *status, cai_stream_t stream_) {
+  CAI_CHECK_ARG(t != nullptr, "cai_rans_encode_batch: NULL table");
+  CAI_CHECK_ARG(B >= 0, "cai_rans_encode_batch: B < 0");
+  if (B == 0) return CAI_OK;
+  CAI_CHECK_ARG(slots && n_words, "cai_rans_encode_batch: NULL output");
+  CAI_CHECK_ARG(str_begin || n_per_string >= 0, "cai_rans_encode_batch: negative string length");
+  CAI_CHECK_ARG((symbols && indexes) || (!str_begin && n_per_string == 0),
+                "cai_rans_encode_batch: NULL symbols / indexes");
+  CAI_CHECK_ARG(slot_words >= 2 && (slot_words % 32) == 0,
+                "cai_rans_encode_batch: slot_words must be a multiple of 32 (use cai_rans_slot_words)");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  rc = ensure_rcp_table(dp.device);
+  if (rc != CAI_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int warps, grid;
+  plan_grid(dp, B, &warps, &grid);
+  if (t->enc_in_smem) {
+    const size_t smem = ((t->enc_bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kEncWarpBytes;
+    CAI_CUDA(cudaFuncSetAttribute(rans_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    rans_encode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, t->enc_bytes, symbols, indexes,
+                                                                 str_begin, n_per_string, B, slots,
+                                                                 slot_words, n_words, status);
+  } else {
+    const size_t smem = static_cast<size_t>(warps) * kEncWarpBytes;
+    rans_encode_kernel<false><<<grid, warps * 32, smem, stream>>>(t->blob, t->enc_bytes, symbols, indexes,
+                                                                  str_begin, n_per_string, B, slots,
+                                                                  slot_words, n_words, status);
+  }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_rans_compact(const uint32_t *slots, int64_t slot_words, const int32_t *n_words, int32_t B,
+                     int64_t *out_begin, uint32_t *out_words, int64_t out_capacity_words,
+                     cai_stream_t stream_) {
+  CAI_CHECK_ARG(B >= 0 && out_begin && n_words, "cai_rans_compact: bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  scan_words_kernel<<<1, 1024, 0, stream>>>(n_words, B, out_begin);
+  CAI_LAUNCH_CHECK();
+  if (out_words && B > 0) {
+    CAI_CHECK_ARG(slots != nullptr, "cai_rans_compact: NULL slots");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc != CAI_OK) return rc;
+    int grid = B < dp.sm_count * 8 ? B : dp.sm_count * 8;
+    compact_kernel<<<grid, 256, 0, stream>>>(slots, slot_words, n_words, B, out_begin, out_words,
+                                             out_capacity_words);
+    CAI_LAUNCH_CHECK();
+  }
+  return CAI_OK;
+}
+
+int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *word_begin,
+                          const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
+                          int32_t B, int32_t *out, uint64_t *state, int32_t resume, int32_t *status,
+                          cai_stream_t stream_) {
+  CAI_CHECK_ARG(t != nullptr, "cai_rans_decode_batch: NULL table");
+  CAI_CHECK_ARG(B >= 0, "cai_rans_decode_batch: B < 0");
+  if (B == 0) return CAI_OK;
+  CAI_CHECK_ARG(words && word_begin, "cai_rans_decode_batch: NULL stream");
+  CAI_CHECK_ARG(!resume || state, "cai_rans_decode_batch: resume needs a state array");
+  CAI_CHECK_ARG(str_begin || n_per_string >= 0, "cai_rans_decode_batch: negative string length");
+  CAI_CHECK_ARG((indexes && out) || (!str_begin && n_per_string == 0),
+                "cai_rans_decode_batch: NULL indexes / out");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int warps, grid;
+  plan_grid(dp, B, &warps, &grid);
+  const uint32_t bytes = static_cast<uint32_t>(t->blob_bytes);
+  if (t->in_smem) {
+    const size_t smem = ((bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kDecWarpBytes;
+    CAI_CUDA(cudaFuncSetAttribute(rans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    rans_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, indexes,
+                                                                 str_begin, n_per_string, B, out, state,
+                                                                 resume, status);
+  } else {
+    const size_t smem = static_cast<size_t>(warps) * kDecWarpBytes;
+    rans_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, indexes,
+                                                                  str_begin, n_per_string, B, out, state,
+                                                                  resume, status);
+  }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+/*
+ * cai_b200.h -- C ABI of libcai_b200.so, the B200 (sm_100a) implementation of CompressAI's codec hot
+ * path.  This is the drop-in boundary: every entry point below replaces one function of the
+ * reference's two native extensions (compressai.ans, compressai._CXX) or one torch op sequence of
+ * compressai.entropy_models / compressai.layers that sits on the compress / decompress / update /
+ * training-forward path.  Paths cited are relative to the reference tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No torch / pybind types.
+ *   - Every pointer is DEVICE memory unless its name ends in _host.
+ *   - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *     results are ordered on that stream.  Calls that must read back a size say so.
+ *   - Return value: 0 = ok, < 0 = error (CAI_E_*); the message is available from cai_last_error()
+ *     (thread local).  No C++ exception crosses this boundary.
+ *   - Per-string / per-row failures detected on the device are written to the `status` arrays
+ *     (0 = ok, CAI_S_* otherwise); they never abort the launch.
+ *   - "coder order" = the order the reference feeds symbols to the coder: for a (N, C, H, W) latent,
+ *     string b is image b flattened as C, H, W (compressai/entropy_models/entropy_models.py:259-267).
+ */
+#ifndef CAI_B200_H_
+#define CAI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define CAI_ABI_VERSION 1
+
+/* host-side error codes */
+#define CAI_OK 0
+#define CAI_E_INVALID (-1)  /* bad argument */
+#define CAI_E_CUDA (-2)     /* CUDA runtime error, see cai_last_error() */
+#define CAI_E_NO_DEVICE (-3)
+#define CAI_E_TOO_LARGE (-4) /* table does not fit the kernel's limits */
+
+/* device-side per-string / per-row status */
+#define CAI_S_OK 0
+#define CAI_S_OVERFLOW 1   /* encoder: slot capacity exceeded */
+#define CAI_S_BAD_INDEX 2  /* cdf index outside [0, K) */
+#define CAI_S_BAD_PMF 3    /* pmf has a negative / non-finite entry (std::domain_error in ops.cpp:46-52) */
+#define CAI_S_ZERO_PMF 4   /* pmf sums to zero (ops.cpp:60-64) */
+#define CAI_S_NO_DONOR 5   /* no symbol left to steal frequency from (assert in ops.cpp:88) */
+#define CAI_S_TRUNCATED 6  /* decoder ran past the end of its string (zeros were fed) */
+
+/* memory layout of a 4-D latent handed to the fused kernels */
+#define CAI_LAYOUT_NCHW 0 /* contiguous N, C, H, W */
+#define CAI_LAYOUT_NHWC 1 /* channels-last storage of a logical N, C, H, W tensor */
+
+typedef void *cai_stream_t;            /* cudaStream_t */
+typedef struct cai_table *cai_table_t; /* opaque: packed CDF tables resident in HBM */
+
+int cai_abi_version(void);
+const char *cai_last_error(void);
+/* Number of SMs / bytes of shared memory per block of the current device (for host-side planning). */
+int cai_device_info(int *sm_count, int *max_smem_per_block);
+
+/* ------------------------------------------------------------------------------------------------
+ * CDF tables.  Replaces the per-call list -> std::vector<std::vector<int>> conversion of
+ * rans_interface.cpp:108-113 / :215-221 (4.2 ms per call for the 64 x 3133 Gaussian table): tables
+ * are packed ONCE per update() into a ragged uint16 blob (+ row metadata + a decode lookup table)
+ * that the coder kernels stage into shared memory with one TMA bulk copy.
+ *   cdfs     int32 [K, Lmax]  (EntropyModel._quantized_cdf)
+ *   cdf_len  int32 [K]        (EntropyModel._cdf_length)
+ *   offsets  int32 [K]        (EntropyModel._offset)
+ * Synchronises `stream` once (it reads back the packed size).
+ * ---------------------------------------------------------------------------------------------- */
+int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t *offsets, int32_t K,
+                     int32_t Lmax, cai_stream_t stream, cai_table_t *out);
+void cai_table_destroy(cai_table_t t);
+/* K, bytes of the blob, decode-LUT buckets per row, 1 if the blob fits shared memory */
+int cai_table_info(cai_table_t t, int32_t *K, int64_t *blob_bytes, int32_t *lut_buckets, int32_t *in_smem);
+
+/* ------------------------------------------------------------------------------------------------
+ * rANS coder.  Bit-exact with ryg_rans rans64.h:59-142 as driven by rans_interface.cpp (16-bit
+ * precision, 4-bit bypass escapes).  One warp-cooperative coder per string.
+ *
+ * Strings: B strings; string b covers elements [str_begin[b], str_begin[b+1]) of `symbols` /
+ * `indexes` when str_begin != NULL (int64 [B+1], device), else [b*n_per_string, (b+1)*n_per_string).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Words a slot must hold so that no input can overflow it (multiple of 32). */
+int64_t cai_rans_slot_words(int64_t n_symbols);
+
+/*
+ * RansEncoder::encode_with_indexes (rans_interface.cpp:202-213) for B strings.
+ *   slots    uint32 [B, slot_words]: string b's words end at slots + (b+1)*slot_words; the byte
+ *            string is the LAST n_words[b] words of the slot, little endian.
+ *   n_words  int32 [B]
+ *   status   int32 [B] or NULL
+ */
+int cai_rans_encode_batch(cai_table_t t, const int32_t *symbols, const int32_t *indexes,
+                          const int64_t *str_begin, int64_t n_per_string, int32_t B, uint32_t *slots,
+                          int64_t slot_words, int32_t *n_words, int32_t *status, cai_stream_t stream);
+
+/*
+ * Gather the used tail of every slot into one contiguous buffer:
+ *   out_begin int64 [B+1] (device, word offsets, written by this call; out_begin[B] = total words)
+ *   out_words uint32 [>= sum(n_words)]   (pass NULL to only compute out_begin)
+ */
+int cai_rans_compact(const uint32_t *slots, int64_t slot_words, const int32_t *n_words, int32_t B,
+                     int64_t *out_begin, uint32_t *out_words, int64_t out_capacity_words,
+                     cai_stream_t stream);
+
+/*
+ * RansDecoder::decode_with_indexes (rans_interface.cpp:215-284) for B strings.
+ *   words      uint32: all strings, word_begin int64 [B+1] gives each string's word range
+ *   out        int32 symbols in coder order (same indexing as `indexes`)
+ *   state      NULL, or uint64 [B, 2] = (rANS state x, next word position) carried between calls:
+ *              RansDecoder::set_stream / decode_stream (rans_interface.cpp:286-359).
+ *              resume = 0: initialise from the first two words (and store the final state if
+ *              state != NULL); resume = 1: continue from `state`.
+ */
+int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *word_begin,
+                          const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
+                          int32_t B, int32_t *out, uint64_t *state, int32_t resume, int32_t *status,
+                          cai_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused quantise + index kernels (HBM-bound, one pass).
+ * Inputs are logical (N, C, HW) latents stored as `layout`; outputs are int32 in CODER ORDER.
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * GaussianConditional: EntropyModel.quantize(y, "symbols", means) (entropy_models.py:155-180) fused
+ * with GaussianConditional.build_indexes(scales) (entropy_models.py:684-689):
+ *   sym = int32(rint(y - mean)),  idx = #{ j < T-1 : !(max(scale, bound) <= table[j]) } counted from
+ *   the left, i.e. (T-1) - sum_j [max(scale, bound) <= table[j]].
+ * means may be NULL.  y / scales / means may be NULL individually to skip that half
+ * (y == NULL -> only indexes; scales == NULL -> only symbols).
+ */
+int cai_gc_quantize_index(const float *y, const float *scales, const float *means,
+                          const float *scale_table, int32_t T, float scale_bound, int32_t layout,
+                          int64_t N, int64_t C, int64_t HW, int32_t *sym, int32_t *idx,
+                          cai_stream_t stream);
+
+/*
+ * EntropyBottleneck.compress front end (entropy_models.py:518-541): sym = int32(rint(x - median[c])),
+ * idx = c.   sym or idx may be NULL.
+ */
+int cai_eb_quantize_index(const float *x, const float *medians, int32_t layout, int64_t N, int64_t C,
+                          int64_t HW, int32_t *sym, int32_t *idx, cai_stream_t stream);
+
+/*
+ * EntropyModel.dequantize (entropy_models.py:188-197) from coder-order int32 symbols to a float
+ * latent stored as `layout`:  out = float(sym) + mean.   Exactly one of means (full tensor, same
+ * layout as out) / medians ([C]) may be non-NULL; both NULL -> plain conversion.
+ */
+int cai_dequantize(const int32_t *sym, const float *means, const float *medians, int32_t layout,
+                   int64_t N, int64_t C, int64_t HW, float *out, cai_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Table build.  pmf_to_quantized_cdf (compressai/cpp_exts/ops/ops.cpp:40-109) for K rows at once with
+ * the caller's row convention of EntropyModel._pmf_to_cdf (entropy_models.py:204-212):
+ *   row k = cat(pmf[k, :pmf_len[k]], tail[k])  ->  cdf[k, :pmf_len[k]+2], zero padded to Lp+2.
+ * pmf float32 [K, Lp]; tail float32 [K]; cdf int32 [K, Lp + 2]; status int32 [K].
+ * tail == NULL: rows are plain pmfs of pmf_len[k] entries -> pmf_len[k]+1 cdf entries
+ * (the bare ops.cpp signature).
+ * ---------------------------------------------------------------------------------------------- */
+int cai_pmf_to_quantized_cdf(const float *pmf, const int32_t *pmf_len, const float *tail, int32_t K,
+                             int32_t Lp, int32_t precision, int32_t *cdf, int32_t *status,
+                             cai_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAI_B200_H_ */
