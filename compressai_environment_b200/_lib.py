@@ -50,6 +50,16 @@ SIGNATURES = {
     "cai_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "cai_pmf_to_quantized_cdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                          c_void_p]),
+    "cai_gc_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_int64, c_void_p,
+                               c_void_p, c_void_p]),
+    "cai_gc_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "cai_eb_forward": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_int32, c_float,
+                               c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cai_eb_backward": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_float, c_int32, c_int64,
+                                c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cai_eb_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_int64, c_int64, c_void_p,
+                              c_void_p, c_void_p]),
 }
 
 _lib = None

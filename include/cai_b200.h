@@ -165,6 +165,53 @@ int cai_pmf_to_quantized_cdf(const float *pmf, const int32_t *pmf_len, const flo
                              int32_t Lp, int32_t precision, int32_t *cdf, int32_t *status,
                              cai_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Likelihood kernels (forward + backward), elementwise over HBM.  All tensors of one call share one
+ * memory layout (any), n = number of elements, except the entropy-bottleneck calls which need the
+ * channel of every element and therefore take (layout, N, C, HW).
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * GaussianConditional.forward (entropy_models.py:669-682) = quantize + _likelihood (:650-667) +
+ * LowerBound (compressai/ops/bound_ops.py:36-42), one pass:
+ *   mode 0 (training): y_hat = y + noise           (means are ignored by quantize("noise"), :161-165)
+ *   mode 1 (eval):     y_hat = rint(y - mean) + mean
+ *   mode 2:            y_hat = y
+ *   lik = max( Phi((.5 - |y_hat - mean|)/s) - Phi((-.5 - |y_hat - mean|)/s), bound_lik ),  s = max(scale, bound_scale)
+ * means / noise / y_hat / lik may be NULL where unused; bound_lik <= 0 disables the likelihood bound.
+ */
+int cai_gc_forward(const float *y, const float *scales, const float *means, const float *noise, int32_t mode,
+                   float bound_scale, float bound_lik, int64_t n, float *y_hat, float *lik, cai_stream_t stream);
+
+/* Backward of the above w.r.t. y_hat, scales and means given g_lik, including
+ * both LowerBound gates.  Output pointers may be NULL. */
+int cai_gc_backward(const float *y_hat, const float *scales, const float *means, const float *g_lik,
+                    float bound_scale, float bound_lik, int64_t n, float *g_y, float *g_scales, float *g_means,
+                    cai_stream_t stream);
+
+/*
+ * EntropyBottleneck.forward (entropy_models.py:471-516) without the two permutes: quantize + _likelihood
+ * (:457-469, built on _logits_cumulative :436-455) + LowerBound.
+ *   tparams float32 [C, P]: per channel, for every layer i: softplus(_matrix_i) row major, _bias_i,
+ *   tanh(_factor_i) (no factor for the last layer).  filters_host: HOST array of the hidden widths
+ *   (default (3, 3, 3, 3) -> P = 58).  medians float32 [C].  mode as in cai_gc_forward.
+ */
+int cai_eb_forward(const float *x, const float *tparams, const int32_t *filters_host, int32_t n_filters,
+                   const float *medians, const float *noise, int32_t mode, float bound_lik, int32_t layout, int64_t N,
+                   int64_t C, int64_t HW, float *out, float *lik, cai_stream_t stream);
+
+/* Backward (Appendix D.3): g_x (layout of x) and g_tparams [C, P] (overwritten) from g_lik and the saved
+ * x_tilde = `out` of the forward.  The sign factor carries no gradient (:464-465). */
+int cai_eb_backward(const float *x_tilde, const float *tparams, const int32_t *filters_host, int32_t n_filters,
+                    const float *g_lik, float bound_lik, int32_t layout, int64_t N, int64_t C, int64_t HW, float *g_x,
+                    float *g_tparams, cai_stream_t stream);
+
+/* _logits_cumulative at per-channel sample points x [C, L] -> out [C, L] (update() :418-421, loss() :431-434).
+ * If g_x != NULL also returns g_x = g_out * d out / d x (parameters are treated as constants). */
+int cai_eb_logits(const float *x, const float *tparams, const int32_t *filters_host, int32_t n_filters,
+                  const float *g_out, int64_t C, int64_t L, float *out, float *g_x, cai_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -29,3 +29,13 @@ def orc():
 
     oracle.build()
     return oracle
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _fp32_library_math():
+    """Keep any torch library op used beside our kernels in true fp32 (TF32 off) for parity checks."""
+    import torch
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield

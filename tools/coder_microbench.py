@@ -1,0 +1,45 @@
+"""C3 microbench: raw coder on B strings x n symbols, default Gaussian table. Device-resident timing."""
+import argparse, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from compressai_environment_b200 import coder, kernels
+from compressai_environment_b200._lib import lib, ptr, check, current_stream
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=4096)
+ap.add_argument("--n", type=int, default=65536)
+ap.add_argument("--t", type=float, default=1.0)
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "cdf.npz"))
+dev = torch.device("cuda")
+table = coder.CdfTable(*(torch.from_numpy(g[k]).to(dev) for k in ("gc_cdf", "gc_len", "gc_off")))
+print(table.info())
+gen = torch.Generator(device=dev).manual_seed(1234)
+tab = torch.from_numpy(g["gc_scale_table"]).to(dev)
+idx = torch.randint(0, 64, (a.B, a.n), generator=gen, device=dev, dtype=torch.int32)
+sym = torch.round(torch.randn((a.B, a.n), generator=gen, device=dev) * tab[idx.long()] * a.t).to(torch.int32)
+def timed(fn, iters):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): r = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, r
+ms, enc = timed(lambda: coder.encode(table, sym, idx), a.iters)
+nsym = a.B * a.n
+nw = int(enc.n_words.sum())
+print(f"encode: {ms:.3f} ms  {nsym/ms/1e6:.2f} Gsym/s  bits/sym={nw*32/nsym:.2f}  algGB/s={(8*nsym+4*nw)/ms/1e6:.1f}")
+strings = enc.to_bytes()
+words, wb, keep = coder.strings_to_device(strings, dev); torch.cuda.synchronize()
+ms, dec = timed(lambda: coder.decode(table, None, idx, device_words=(words, wb)), a.iters)
+print(f"decode: {ms:.3f} ms  {nsym/ms/1e6:.2f} Gsym/s  algGB/s={(8*nsym+4*nw)/ms/1e6:.1f}")
+assert torch.equal(dec, sym)
+y = torch.randn((a.B, a.n), generator=gen, device=dev) * 5
+sc = torch.exp(torch.rand((a.B, a.n), generator=gen, device=dev) * 8 - 3)
+ms, _ = timed(lambda: kernels.gc_quantize_index(y.view(a.B, a.n, 1), sc.view(a.B, a.n, 1), None, tab, 0.11), a.iters)
+print(f"gc_quantize_index nchw: {ms:.3f} ms  {16*nsym/ms/1e6:.1f} GB/s")
+if a.n % 192 == 0:
+    y4 = y.view(a.B, 192, -1, 1).contiguous(memory_format=torch.channels_last); s4 = sc.view(a.B, 192, -1, 1).contiguous(memory_format=torch.channels_last)
+    ms, _ = timed(lambda: kernels.gc_quantize_index(y4, s4, None, tab, 0.11), a.iters)
+    print(f"gc_quantize_index nhwc: {ms:.3f} ms  {16*nsym/ms/1e6:.1f} GB/s")
