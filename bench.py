@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the codec hot path (BASELINE.json: compress+decompress MP/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Workload (BASELINE.json configs[1], "C2"): bmshj2018-hyperprior q4 (N=128, M=192), `--batch` (default 256)
+synthetic 768x512 RGB images per GPU, random-init weights (seed 0) with the deterministic latent / scale
+amplification of SURVEY.md 8(d)(ii) so that the Gaussian-conditional coder sees non-degenerate symbols.
+One step = compress + decompress of the whole batch.  Prints ONE JSON line on rank 0.
+
+  value    : device-resident pipeline (inputs in HBM, strings stay in HBM), CUDA-event timed, max over ranks
+  e2e      : the public API with HOST buffers: pinned images -> model.compress() -> bytes on the host ->
+             model.decompress() -> reconstruction on the host (H2D / D2H inside the timed region)
+  roofline : the rANS decode kernel (dominant kernel written in this repo), algorithmic bytes / CUDA-event time
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref) on the host cores, bounded sample of the same workload
+
+--impl reference times the reference's own CPU implementation (model.compress/decompress, torch CPU +
+compressai.ans C++ coder) with all host threads on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 512, 768
+N_CH, M_CH = 128, 192
+GAIN_Y, GAIN_S = 64.0, 256.0
+METRIC = "compress+decompress throughput, bmshj2018-hyperprior q4, 768x512 images"
+UNIT = "MP/s"
+
+
+def amplify(net):
+    import torch
+
+    with torch.no_grad():
+        net.g_a[6].weight.mul_(GAIN_Y)
+        net.g_a[6].bias.mul_(GAIN_Y)
+        net.h_s[4].weight.mul_(GAIN_S)
+        net.h_s[4].bias.mul_(GAIN_S)
+
+
+def make_images(batch, seed=0):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, 3, H, W, generator=g)
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def reference_arm(args, rank):
+    """The UNMODIFIED reference on the host cores (oracle/_ref), same model state, bounded sample per step."""
+    import torch
+
+    from oracle import oracle as orc
+
+    if not orc.have_ref():
+        orc.build_ref()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc.import_ref()
+    from compressai.zoo import bmshj2018_hyperprior as ref_hyperprior
+
+    torch.manual_seed(0)
+    net = ref_hyperprior(quality=4, pretrained=False).eval()
+    amplify(net)
+    net.update(force=True)
+    sample = max(1, args.ref_sample)
+    x = make_images(sample)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            enc = net.compress(x)
+            dec = net.decompress(enc["strings"], enc["shape"])
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    assert dec["x_hat"].shape == x.shape
+    T = sum(times) / len(times)
+    mp = sample * H * W / 1e6
+    val = mp / T
+    nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
+    return {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 bmshj2018-hyperprior q4 768x512 (reference CPU path)", "batch_per_step": sample,
+                   "gain_y": GAIN_Y, "gain_s": GAIN_S, "bytes_per_image": nbytes / sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{sample} images per step, torch {torch.__version__} CPU + compressai.ans C++ coder"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def cpu_baseline_sample(n_images):
+    """cpu_baseline leg of the default run: reference model on the host cores, one bounded sample."""
+    import torch
+
+    from oracle import oracle as orc
+
+    cores = os.cpu_count() or 1
+    if not orc.have_ref() and not orc.build_ref():
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "oracle/_ref missing"}
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    orc.import_ref()
+    from compressai.zoo import bmshj2018_hyperprior as ref_hyperprior
+
+    torch.manual_seed(0)
+    net = ref_hyperprior(quality=4, pretrained=False).eval()
+    amplify(net)
+    net.update(force=True)
+    x = make_images(n_images)
+    with torch.no_grad():
+        net.compress(x[:1])  # warm-up
+        t0 = time.perf_counter()
+        enc = net.compress(x)
+        net.decompress(enc["strings"], enc["shape"])
+        dt = time.perf_counter() - t0
+    torch.set_num_threads(prev)
+    return {"value": n_images * H * W / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{n_images} images, one compress+decompress ({dt:.1f} s), all host threads"}, enc
+
+
+def ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import compressai_environment_b200 as cai
+    from compressai_environment_b200 import _lib, coder
+    from compressai_environment_b200.zoo import bmshj2018_hyperprior
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    torch.manual_seed(0)
+    net = bmshj2018_hyperprior(quality=4)
+    amplify(net)
+    net = net.to(dev).eval()
+    net.update(force=True)
+
+    B, mb = args.batch, min(args.micro_batch, args.batch)
+    x_host = make_images(B).pin_memory()
+    x_dev = x_host.to(dev)
+    mp_step = B * H * W / 1e6
+
+    def step_device():
+        outs = []
+        for i in range(0, B, mb):
+            enc = net.compress_to_device(x_dev[i:i + mb])
+            dec = net.decompress_from_device(enc["strings"], enc["shape"])
+            outs.append((enc, dec))
+        return outs
+
+    def step_e2e():
+        h2d = d2h = 0
+        for i in range(0, B, mb):
+            xb = x_host[i:i + mb].to(dev, non_blocking=True)
+            h2d += xb.numel() * 4
+            enc = net.compress(xb)
+            nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
+            d2h += nbytes
+            dec = net.decompress(enc["strings"], enc["shape"])
+            h2d += nbytes
+            xh = dec["x_hat"].to("cpu", non_blocking=False)
+            d2h += xh.numel() * 4
+        return h2d, d2h, nbytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        coder.TIMING = {}
+        launches0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            outs = step_device()
+        e1.record()
+        barrier()
+        launches = _lib.LAUNCHES - launches0
+        timing, coder.TIMING = coder.TIMING, None
+        ms = e0.elapsed_time(e1) / args.steps
+        clocks = sampler.stop() if rank == 0 else None
+
+        # roofline of the dominant kernel written here: rANS decode of the y strings
+        dec_ms = sorted(a.elapsed_time(b) for a, b in timing.get("rans_decode_kernel", []))
+        enc_ms = sorted(a.elapsed_time(b) for a, b in timing.get("rans_encode_kernel", []))
+        y_enc = outs[-1][0]["strings"][0]
+        n_sym_y = mb * M_CH * (H // 16) * (W // 16)
+        payload = int(y_enc.n_words.sum().item()) * 4
+        # decode: 4 B/sym index read + payload read + 4 B/sym symbol write
+        alg_bytes = 8 * n_sym_y + payload
+        big = [t for t in dec_ms if t >= 0.5 * dec_ms[-1]] if dec_ms else []
+        dec_avg = sum(big) / len(big) if big else None
+
+        # e2e through the public API with host buffers
+        for _ in range(1):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h2d, d2h, _ = step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    achieved = alg_bytes / (dec_avg * 1e-3) / 1e9 if dec_avg else None
+    cpu = {"value": None}
+    if not args.no_cpu_baseline:
+        try:
+            cpu, _ = cpu_baseline_sample(args.cpu_sample)
+        except Exception as e:  # the baseline must never take the GPU line down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    line = {
+        "metric": METRIC, "value": world * mp_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 bmshj2018-hyperprior q4 (N=128,M=192) 768x512, random-init seed 0, amplified",
+                   "batch_per_gpu": B, "micro_batch": mb, "gain_y": GAIN_Y, "gain_s": GAIN_S,
+                   "l2": "inputs_larger_than_L2 (302 MB images, >1 GB activations per micro-batch)",
+                   "y_bits_per_symbol": payload * 8 / n_sym_y, "parallelism": f"batch-sharded x{world}, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": world * mp_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "rans_decode_kernel (y strings)", "bound": "hbm", "achieved": achieved, "peak": hbm,
+                     "unit": "GB/s", "frac": (achieved / hbm) if achieved else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                     "avg_launch_ms": dec_avg, "alg_bytes_per_launch": alg_bytes,
+                     "encode_avg_launch_ms": (sum(enc_ms[len(enc_ms) // 2:]) / max(1, len(enc_ms) - len(enc_ms) // 2))
+                     if enc_ms else None},
+        "cpu_baseline": cpu,
+    }
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=8, help="images per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(args, rank)), flush=True)
+        return
+    line = ours(args, rank, world)
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,7 @@ SIGNATURES = {
     "cai_rans_encode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_void_p]),
     "cai_rans_compact": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
-    "cai_rans_decode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+    "cai_rans_decode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
                                       c_void_p, c_int32, c_void_p, c_void_p]),
     "cai_gc_quantize_index": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_int64,
                                       c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -93,7 +93,17 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+# kernels launched per successful C-ABI call (bench.py reports the total as "gpu_launches")
+KERNELS_PER_CALL = {"cai_table_create": 3, "cai_rans_encode_batch": 1, "cai_rans_compact": 2,
+                    "cai_rans_decode_batch": 1, "cai_gc_quantize_index": 1, "cai_eb_quantize_index": 1,
+                    "cai_dequantize": 1, "cai_pmf_to_quantized_cdf": 1, "cai_gc_forward": 1, "cai_gc_backward": 1,
+                    "cai_eb_forward": 1, "cai_eb_backward": 1, "cai_eb_logits": 1}
+LAUNCHES = 0
+
+
 def check(rc: int, what: str = "") -> None:
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = lib().cai_last_error().decode("utf-8", "replace")
         raise CaiError(f"{what or 'libcai_b200'} failed (rc={rc}): {msg}")

@@ -17,6 +17,29 @@ from . import _lib
 from ._lib import check, current_stream, lib, ptr, require_cuda
 
 
+# Optional profiling hook used by bench.py: when set to a dict, every coder launch appends a
+# (start_event, end_event) pair under its kernel name, recorded on the launching stream.
+TIMING = None
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.e1.record()
+            TIMING.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 class CdfTable:
     """Packed CDF tables resident in HBM (``cai_table_t``).  Built once per ``update()``."""
 
@@ -74,6 +97,14 @@ class EncodedBatch:
     def __init__(self, slots, n_words, status, slot_w):
         self.slots, self.n_words, self.status, self.slot_w = slots, n_words, status, slot_w
 
+    def device_words(self):
+        """(words, word_begin) usable as ``decode(..., device_words=...)`` without leaving the device: the
+        strings are read in place from the slots (begin[b] = end of slot b - n_words[b])."""
+        B = self.n_words.numel()
+        begin = torch.arange(1, B + 1, device=self.slots.device, dtype=torch.int64) * self.slot_w
+        begin -= self.n_words.to(torch.int64)
+        return self.slots.reshape(-1), begin, self.n_words
+
     def to_bytes(self) -> List[bytes]:
         B = self.n_words.numel()
         if B == 0:
@@ -112,7 +143,7 @@ def encode(table: CdfTable, symbols: torch.Tensor, indexes: torch.Tensor) -> Enc
     slots = torch.empty((max(B, 1), sw), dtype=torch.int32, device=dev)
     n_words = torch.empty(B, dtype=torch.int32, device=dev)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("rans_encode_kernel"):
         check(lib().cai_rans_encode_batch(table.handle, ptr(symbols), ptr(indexes), None, n, B, ptr(slots), sw,
                                           ptr(n_words), ptr(status), current_stream()), "cai_rans_encode_batch")
     return EncodedBatch(slots, n_words, status, sw)
@@ -148,12 +179,14 @@ def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, sta
         if len(strings) != B:
             raise ValueError("Invalid strings or indexes parameters")
         words, wb, keep = strings_to_device(strings, dev)
+        wcount = None
     else:
-        words, wb = device_words
+        words, wb = device_words[0], device_words[1]
+        wcount = device_words[2] if len(device_words) > 2 else None
         keep = None
     status = torch.zeros(B, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        check(lib().cai_rans_decode_batch(table.handle, ptr(words), ptr(wb), ptr(indexes), None, n, B, ptr(out),
+    with torch.cuda.device(dev), _Timed("rans_decode_kernel"):
+        check(lib().cai_rans_decode_batch(table.handle, ptr(words), ptr(wb), ptr(wcount), ptr(indexes), None, n, B, ptr(out),
                                           ptr(state), 1 if resume else 0, ptr(status), current_stream()),
               "cai_rans_decode_batch")
     if keep is not None:

@@ -319,7 +319,8 @@ struct WordFeed {
 template <bool kSmem>
 __global__ void __launch_bounds__(1024, 1)
 rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, const uint32_t *__restrict__ words,
-                   const int64_t *__restrict__ word_begin, const int32_t *__restrict__ indexes,
+                   const int64_t *__restrict__ word_begin, const int32_t *__restrict__ word_count,
+                   const int32_t *__restrict__ indexes,
                    const int64_t *__restrict__ str_begin, int64_t n_per_string, int32_t B,
                    int32_t *__restrict__ out, uint64_t *__restrict__ state, int32_t resume,
                    int32_t *__restrict__ status) {
@@ -355,7 +356,7 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
 
     WordFeed wf;
     wf.w = words + word_begin[b];
-    wf.nw = word_begin[b + 1] - word_begin[b];
+    wf.nw = word_count ? static_cast<int64_t>(word_count[b]) : (word_begin[b + 1] - word_begin[b]);
     wf.lane = lane;
     uint64_t x;
     if (resume && state) {
@@ -587,7 +588,7 @@ int cai_rans_compact(const uint32_t *slots, int64_t slot_words, const int32_t *n
 }
 
 int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *word_begin,
-                          const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
+                          const int32_t *word_count, const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
                           int32_t B, int32_t *out, uint64_t *state, int32_t resume, int32_t *status,
                           cai_stream_t stream_) {
   CAI_CHECK_ARG(t != nullptr, "cai_rans_decode_batch: NULL table");
@@ -609,12 +610,12 @@ int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *w
     const size_t smem = ((bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kDecWarpBytes;
     CAI_CUDA(cudaFuncSetAttribute(rans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    rans_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, indexes,
+    rans_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, word_count, indexes,
                                                                  str_begin, n_per_string, B, out, state,
                                                                  resume, status);
   } else {
     const size_t smem = static_cast<size_t>(warps) * kDecWarpBytes;
-    rans_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, indexes,
+    rans_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, word_count, indexes,
                                                                   str_begin, n_per_string, B, out, state,
                                                                   resume, status);
   }

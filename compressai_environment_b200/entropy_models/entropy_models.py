@@ -524,19 +524,21 @@ class EntropyBottleneck(EntropyModel):
         x_hat = kernels.dequantize(sym, None, self._get_medians(), tuple(xs.shape), fmt).reshape(x.shape)
         return enc, x_hat
 
-    def decompress(self, strings, size, memory_format=torch.contiguous_format):
-        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+    def decompress(self, strings, size, memory_format=torch.contiguous_format, device_words=None):
+        n_strings = len(strings) if device_words is None else int(device_words[2].numel())
+        output_size = (n_strings, self._quantized_cdf.size(0), *size)
         self._check_cdf_size()
         self._check_cdf_length()
         self._check_offsets_size()
-        if not isinstance(strings, (tuple, list)):
+        if device_words is None and not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         dev = self._quantized_cdf.device
         require_cuda(self._quantized_cdf, "EntropyBottleneck buffers")
         N, C = output_size[0], output_size[1]
         HW = int(np.prod(output_size[2:])) if len(output_size) > 2 else 1
         idx = kernels.channel_indexes(N, C, HW, dev)
-        sym = coder.decode(self._table(), list(strings), idx)
+        sym = coder.decode(self._table(), None if device_words is not None else list(strings), idx,
+                           device_words=device_words)
         shape = output_size if len(output_size) > 2 else (N, C, 1)
         out = kernels.dequantize(sym, None, self._get_medians(), shape, memory_format)
         return out.reshape(output_size).type(self.quantiles.dtype)
@@ -647,11 +649,12 @@ class GaussianConditional(EntropyModel):
         return coder.encode(self._table(), sym, idx), idx
 
     def decompress_from_scales(self, strings, scales: Tensor, means: Optional[Tensor] = None,
-                               memory_format=torch.channels_last) -> Tensor:
+                               memory_format=torch.channels_last, device_words=None) -> Tensor:
         """build_indexes + decode + dequantize for the whole batch."""
         self._check_cdf_size()
         self._check_cdf_length()
         self._check_offsets_size()
         _, idx = kernels.gc_quantize_index(None, scales, None, self.scale_table, self._bound_scale())
-        sym = coder.decode(self._table(), list(strings), idx)
+        sym = coder.decode(self._table(), None if device_words is not None else list(strings), idx,
+                           device_words=device_words)
         return kernels.dequantize(sym, means, None, tuple(scales.shape), memory_format)

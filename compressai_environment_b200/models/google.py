@@ -193,6 +193,24 @@ class ScaleHyperprior(CompressionModel):
         x_hat = self.g_s(y_hat).clamp_(0, 1)
         return {"x_hat": x_hat}
 
+    # ---- device-resident variants (same kernels, strings never leave HBM): used for kernel-only timing ----
+    def compress_to_device(self, x):
+        y = self.g_a(_nhwc(x))
+        z = self.h_a(self._hyper_in(y))
+        z_enc, z_hat = self.entropy_bottleneck.compress_symbols(z)
+        scales_hat, means_hat = self._params(z_hat)
+        y_enc, _ = self.gaussian_conditional.compress_from_scales(y, scales_hat, means_hat)
+        return {"strings": [y_enc, z_enc], "shape": z.size()[-2:]}
+
+    def decompress_from_device(self, enc, shape):
+        y_enc, z_enc = enc
+        z_hat = self.entropy_bottleneck.decompress(None, shape, memory_format=_CL, device_words=z_enc.device_words())
+        scales_hat, means_hat = self._params(z_hat)
+        y_hat = self.gaussian_conditional.decompress_from_scales(None, scales_hat, means_hat,
+                                                                 device_words=y_enc.device_words())
+        x_hat = self.g_s(y_hat).clamp_(0, 1)
+        return {"x_hat": x_hat}
+
 
 class MeanScaleHyperprior(ScaleHyperprior):
     r"""Scale Hyperprior with non zero-mean Gaussian conditionals (Minnen et al., NeurIPS 2018)."""

@@ -108,7 +108,10 @@ int cai_rans_compact(const uint32_t *slots, int64_t slot_words, const int32_t *n
 
 /*
  * RansDecoder::decode_with_indexes (rans_interface.cpp:215-284) for B strings.
- *   words      uint32: all strings, word_begin int64 [B+1] gives each string's word range
+ *   words      uint32: all strings; string b starts at word_begin[b] (int64, device) and has
+ *              word_count[b] words (int32 [B]); word_count == NULL: word_begin has B+1 entries and
+ *              string b ends where string b+1 begins (packed layout of cai_rans_compact).
+ *              With word_count the strings may be read in place from the encoder's slots.
  *   out        int32 symbols in coder order (same indexing as `indexes`)
  *   state      NULL, or uint64 [B, 2] = (rANS state x, next word position) carried between calls:
  *              RansDecoder::set_stream / decode_stream (rans_interface.cpp:286-359).
@@ -116,7 +119,7 @@ int cai_rans_compact(const uint32_t *slots, int64_t slot_words, const int32_t *n
  *              state != NULL); resume = 1: continue from `state`.
  */
 int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *word_begin,
-                          const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
+                          const int32_t *word_count, const int32_t *indexes, const int64_t *str_begin, int64_t n_per_string,
                           int32_t B, int32_t *out, uint64_t *state, int32_t resume, int32_t *status,
                           cai_stream_t stream);
 
