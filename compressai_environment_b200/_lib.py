@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int8, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcai_b200.so")
@@ -27,6 +27,15 @@ STATUS_TEXT = {
     5: "Invalid `pmf`: no symbol to steal frequency from",
     6: "decoder ran past the end of the string",
 }
+
+class ConvDesc(Structure):
+    """Mirror of ``cai_conv_desc`` (include/cai_b200.h)."""
+    _fields_ = ([(n, c_void_p) for n in ("a_hi", "a_lo", "w_packed", "bias", "aux_hi", "aux_lo", "out_f32", "out_hi",
+                                         "out_lo", "sq_hi", "sq_lo", "abs_hi", "abs_lo")]
+                + [(n, c_int32) for n in ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "Hp", "Wp", "os", "o0y", "o0x", "is_",
+                                          "ntaps", "BN", "epilogue")]
+                + [("clamp_lo", c_float), ("clamp_hi", c_float), ("dy", c_int8 * 32), ("dx", c_int8 * 32)])
+
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/cai_b200.h
 # (tests/test_abi.py cross-checks this table against the header and the built library).
@@ -60,6 +69,10 @@ SIGNATURES = {
                                 c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cai_eb_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_int64, c_int64, c_void_p,
                               c_void_p, c_void_p]),
+    "cai_conv_gemm": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "cai_split_planes": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cai_im2col_split": (c_int, [c_void_p] + [c_int32] * 11 + [c_void_p, c_void_p, c_void_p]),
+    "cai_col2im": (c_int, [c_void_p, c_void_p] + [c_int32] * 11 + [c_float, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -97,7 +110,8 @@ def lib() -> ctypes.CDLL:
 KERNELS_PER_CALL = {"cai_table_create": 3, "cai_rans_encode_batch": 1, "cai_rans_compact": 2,
                     "cai_rans_decode_batch": 1, "cai_gc_quantize_index": 1, "cai_eb_quantize_index": 1,
                     "cai_dequantize": 1, "cai_pmf_to_quantized_cdf": 1, "cai_gc_forward": 1, "cai_gc_backward": 1,
-                    "cai_eb_forward": 1, "cai_eb_backward": 1, "cai_eb_logits": 1}
+                    "cai_eb_forward": 1, "cai_eb_backward": 1, "cai_eb_logits": 1, "cai_conv_gemm": 1,
+                    "cai_split_planes": 1, "cai_im2col_split": 1, "cai_col2im": 1}
 LAUNCHES = 0
 
 

@@ -1,0 +1,580 @@
+// conv.cu -- tcgen05 implicit-GEMM convolution / transposed convolution / GDN for sm_100a.
+//
+// What it replaces (reference tree): the cuDNN / ATen kernels behind
+//   compressai/models/utils.py:128-146   conv (k5 s2 p2, k3 s1 p1) and deconv (k5 s2 p2 op1)
+//   compressai/layers/gdn.py:77-92       GDN / IGDN  (1x1 conv of x^2 with gamma, + beta, rsqrt / sqrt, * x)
+//   compressai/models/google.py:134-152, :219-254, :339-353   the g_a / g_s / h_a / h_s stacks
+//
+// Formulation.  Every layer is D[m, n] = sum_k A[m, k] * B[n, k] with
+//   m = output pixel of one output "phase" grid, n = output channel, k = (tap, input channel).
+//   conv:    one phase, taps = all (ky, kx), input pixel = (i * stride + ky - pad, j * stride + kx - pad)
+//   deconv:  4 phases (oy%2, ox%2); phase (py, px) uses the taps with ky = (py + pad) mod 2 (9/6/6/4 taps),
+//            input pixel = (i + (py + pad - ky) / 2, j + ...) -- a stride-1 gather, no zero insertion
+//   GDN:     1x1 "conv" of x^2 with gamma, epilogue out = x * rsqrt(acc + beta)   (IGDN: * sqrt)
+//
+// Precision.  Operands are fp32 values SPLIT into two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); each
+// k16 step issues three tcgen05.mma (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM), which keeps ~16
+// mantissa bits per operand: results agree with an fp32 reference to ~1e-5 relative, which the symbol
+// rounding downstream needs.  Activations travel between layers as the two bf16 planes (same bytes as
+// fp32), so the A operand is a pure copy: cp.async (LDGSTS, 16 B = 8 channels of one pixel, zero-filled
+// for padding) straight into the UMMA canonical K-major layout; weights are pre-packed on the host in
+// that same layout and arrive with one TMA bulk copy per stage.
+//
+// CTA = 5 warps: warps 0-3 produce the A tile (thread = pixel row) and later run the epilogue (thread =
+// TMEM lane), warp 4 issues the MMAs (one elected lane) and owns the TMEM allocation.  smem ring of
+// kStages (A hi/lo 32 KB + B hi/lo BN*256 B per stage), mbarrier full/empty per stage, accumulator
+// 128 lanes x BN columns of TMEM, drained with tcgen05.ld.32x32b.x16.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cai {
+
+constexpr int kBM = 128;          // pixels per tile (UMMA M)
+constexpr int kBK = 64;           // k elements per stage (4 x UMMA_K=16)
+constexpr int kProducerThreads = 128;
+constexpr int kConvThreads = 160;
+constexpr int kMaxTaps = 32;
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+struct ConvKernelParams {
+  const __nv_bfloat16 *a_hi, *a_lo;  // [N, H, W, Cin] bf16 planes
+  const unsigned char *w_packed;     // [n_tiles][ksteps][hi | lo] each BN x 64 bf16, canonical layout
+  const float *bias;                 // [Cout] or NULL
+  const __nv_bfloat16 *aux_hi, *aux_lo;  // [M_out_pixels, Cout] planes for the GDN finalize, or NULL
+  float *out_f32;                    // [N, Ho, Wo, Cout] or NULL
+  __nv_bfloat16 *out_hi, *out_lo;    // split planes of the output, or NULL
+  __nv_bfloat16 *sq_hi, *sq_lo;      // split planes of output^2, or NULL
+  __nv_bfloat16 *abs_hi, *abs_lo;    // split planes of |output|, or NULL
+  int N, H, W, Cin, Ho, Wo, Cout;
+  int Hp, Wp;                        // phase grid
+  int os, o0y, o0x;                  // output pixel = (i * os + o0y, j * os + o0x)
+  int is;                            // input pixel  = (i * is + dy[t], j * is + dx[t])
+  int ntaps;
+  int kchunks;                       // ceil(Cin / 64)
+  int BN;                            // output channels per tile (multiple of 16, <= 256)
+  int epilogue;                      // 0 linear, 1 relu, 2 leaky relu (0.01), 3 gdn (aux * rsqrt), 4 igdn (aux * sqrt)
+  float clamp_lo, clamp_hi;          // applied when clamp_lo < clamp_hi
+  int stages;
+  int8_t dy[kMaxTaps], dx[kMaxTaps];
+};
+
+__device__ __forceinline__ void spin_fail() {
+  asm volatile("trap;");
+}
+
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t phase) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(phase)
+        : "memory");
+    if (!done && ++spins > kSpinLimit) spin_fail();
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: canonical ((8, n), 2) : ((16 B, SBO), LBO)
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  return d;         // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+struct Pack8 {
+  uint4 hi, lo;
+};
+__device__ __forceinline__ Pack8 split8(const float *v) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+  Pack8 p;
+  p.hi = *reinterpret_cast<uint4 *>(h);
+  p.lo = *reinterpret_cast<uint4 *>(l);
+  return p;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[4];
+  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const int stages = p.stages;
+  const uint32_t a_plane = kBM * kBK * 2;          // 16 KB: one bf16 plane of the A tile
+  const uint32_t b_plane = static_cast<uint32_t>(BN) * kBK * 2;
+  const uint32_t stage_bytes = 2 * a_plane + 2 * b_plane;
+  const int ksteps = p.ntaps * p.kchunks;
+  const int64_t M_total = static_cast<int64_t>(p.N) * p.Hp * p.Wp;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * kBM;
+  const int n_tile = blockIdx.y;
+  const int n0 = n_tile * BN;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp < 4) {
+    // ===================== producers: thread = pixel row of the tile =====================
+    const int r = tid;
+    const int64_t m = m0 + r;
+    const bool row_ok = m < M_total;
+    int n_img = 0, pi = 0, pj = 0;
+    if (row_ok) {
+      const int64_t per = static_cast<int64_t>(p.Hp) * p.Wp;
+      n_img = static_cast<int>(m / per);
+      const int rem = static_cast<int>(m - n_img * per);
+      pi = rem / p.Wp;
+      pj = rem - pi * p.Wp;
+    }
+    const uint32_t row_off = (static_cast<uint32_t>(r) >> 3) * 128u + (static_cast<uint32_t>(r) & 7u) * 16u;
+    const unsigned char *wbase = p.w_packed + static_cast<size_t>(n_tile) * ksteps * (2 * b_plane);
+
+    auto issue = [&](int ks) {
+      const int s = ks % stages;
+      const int t = ks / p.kchunks, kc = ks - t * p.kchunks;
+      unsigned char *sa = smem + static_cast<size_t>(s) * stage_bytes;
+      const int iy = pi * p.is + p.dy[t], ix = pj * p.is + p.dx[t];
+      const bool ok = row_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      const int64_t pix = ok ? ((static_cast<int64_t>(n_img) * p.H + iy) * p.W + ix) : 0;
+      const __nv_bfloat16 *gh = p.a_hi + pix * p.Cin + kc * kBK;
+      const __nv_bfloat16 *gl = p.a_lo + pix * p.Cin + kc * kBK;
+      const int kleft = p.Cin - kc * kBK;  // valid k elements in this chunk (may be < 64 on the tail)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t nbytes = (ok && c * 8 < kleft) ? 16u : 0u;
+        const uint32_t so = static_cast<uint32_t>(c) * (kBM * 16u) + row_off;
+        cp_async16(sa + so, nbytes ? static_cast<const void *>(gh + c * 8) : static_cast<const void *>(p.a_hi), nbytes);
+        cp_async16(sa + a_plane + so, nbytes ? static_cast<const void *>(gl + c * 8) : static_cast<const void *>(p.a_lo),
+                   nbytes);
+      }
+      if (tid == 0) {
+        mbar_expect_tx(&full_bar[s], 2 * b_plane);
+        tma_bulk_g2s(sa + 2 * a_plane, wbase + static_cast<size_t>(ks) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
+      }
+    };
+
+    // software pipeline: keep (stages - 1) k-steps of cp.async in flight
+    const int lag = stages - 1;
+    for (int ks = 0; ks < ksteps + lag; ++ks) {
+      if (ks < ksteps) {
+        const int s = ks % stages;
+        if (ks >= stages) mbar_wait_bounded(&empty_bar[s], ((ks / stages) - 1) & 1);
+        issue(ks);
+      }
+      cp_async_commit();
+      if (ks >= lag) {
+        // k-step (ks - lag) has landed for this thread
+        if (lag == 1) cp_async_wait<1>();
+        else if (lag == 2) cp_async_wait<2>();
+        else cp_async_wait<3>();
+        fence_async_proxy();
+        mbar_arrive(&full_bar[(ks - lag) % stages]);
+      }
+    }
+
+    // ===================== epilogue: thread = TMEM lane = pixel row =====================
+    mbar_wait_bounded(&acc_bar, 0);
+    tc_fence_after();
+    int64_t opix = 0;
+    if (row_ok) {
+      const int oy = pi * p.os + p.o0y, ox = pj * p.os + p.o0x;
+      opix = (static_cast<int64_t>(n_img) * p.Ho + oy) * p.Wo + ox;
+    }
+    const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
+      if (!row_ok) continue;
+      const int cg = n0 + c0;  // global output channel of raw[0]
+      if (cg >= p.Cout) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(raw[i]);
+        if (p.bias && cg + i < p.Cout) a += __ldg(p.bias + cg + i);
+        v[i] = a;
+      }
+      const int64_t obase = opix * p.Cout + cg;
+      if (p.epilogue == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (p.epilogue == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+      } else if (p.epilogue >= 3) {
+        const uint4 *ah = reinterpret_cast<const uint4 *>(p.aux_hi + obase);
+        const uint4 *al = reinterpret_cast<const uint4 *>(p.aux_lo + obase);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 qh = __ldg(ah + h), ql = __ldg(al + h);
+          const __nv_bfloat16 *bh = reinterpret_cast<const __nv_bfloat16 *>(&qh);
+          const __nv_bfloat16 *bl = reinterpret_cast<const __nv_bfloat16 *>(&ql);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = __bfloat162float(bh[i]) + __bfloat162float(bl[i]);
+            const float nrm = v[h * 8 + i];
+            v[h * 8 + i] = (p.epilogue == 3) ? x * rsqrtf(nrm) : x * sqrtf(nrm);
+          }
+        }
+      }
+      if (p.clamp_lo < p.clamp_hi) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], p.clamp_lo), p.clamp_hi);
+      }
+      // Cout is a multiple of 16 for every tensor-core layer (host pads otherwise), so 16-wide stores are aligned
+      if (p.out_f32) {
+        float4 *o = reinterpret_cast<float4 *>(p.out_f32 + obase);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (p.out_hi) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const Pack8 pk = split8(v + 8 * h);
+          reinterpret_cast<uint4 *>(p.out_hi + obase)[h] = pk.hi;
+          reinterpret_cast<uint4 *>(p.out_lo + obase)[h] = pk.lo;
+        }
+      }
+      if (p.sq_hi) {
+        float s[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] = v[i] * v[i];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const Pack8 pk = split8(s + 8 * h);
+          reinterpret_cast<uint4 *>(p.sq_hi + obase)[h] = pk.hi;
+          reinterpret_cast<uint4 *>(p.sq_lo + obase)[h] = pk.lo;
+        }
+      }
+      if (p.abs_hi) {
+        float s[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] = fabsf(v[i]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const Pack8 pk = split8(s + 8 * h);
+          reinterpret_cast<uint4 *>(p.abs_hi + obase)[h] = pk.hi;
+          reinterpret_cast<uint4 *>(p.abs_lo + obase)[h] = pk.lo;
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer (warp 4, one elected lane) =====================
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                           (static_cast<uint32_t>(kBM >> 4) << 24);
+    const uint32_t lbo_a = kBM * 16u, lbo_b = static_cast<uint32_t>(BN) * 16u;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int s = ks % stages;
+      mbar_wait_bounded(&full_bar[s], (ks / stages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + a_plane, b_hi = sa + 2 * a_plane, b_lo = b_hi + b_plane;
+#pragma unroll
+        for (int kk = 0; kk < kBK / 16; ++kk) {
+          const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, 128);
+          const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, 128);
+          const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
+          const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, 128);
+          umma_bf16(tmem_base, dah, dbh, idesc, (ks | kk) ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);                    // frees the smem stage when the MMAs have read it
+        if (ks == ksteps - 1) umma_commit(&acc_bar);   // accumulator complete
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- helper kernels ------------------------------------------------------------------------------------
+
+// fp32 (NCHW or NHWC) -> split bf16 NHWC planes, optionally padding channels to Cpad with zeros
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float *__restrict__ x, int layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad,
+                    __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+  const int64_t total = N * HW * Cpad;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t c = i % Cpad, pix = i / Cpad;
+    float v = 0.f;
+    if (c < C) {
+      const int64_t n = pix / HW, hw = pix - n * HW;
+      v = (layout == CAI_LAYOUT_NHWC) ? x[pix * C + c] : x[(n * C + c) * HW + hw];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// im2col for tiny Cin (first layer, Cin = 3): [N, H, W, C] fp32 (any layout) -> split planes [N*Ho*Wo, Kpad]
+// with k = (ky * ks + kx) * C + c, zero padded to Kpad.
+__global__ void __launch_bounds__(256)
+im2col_split_kernel(const float *__restrict__ x, int layout, int N, int C, int H, int W, int Ho, int Wo, int ksz,
+                    int stride, int pad, int Kpad, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Kpad;
+  const int64_t gs = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int K = ksz * ksz * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    const int k = static_cast<int>(i % Kpad);
+    const int64_t pix = i / Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, t = k / C, ky = t / ksz, kx = t - ky * ksz;
+      const int ox = static_cast<int>(pix % Wo);
+      const int64_t r = pix / Wo;
+      const int oy = static_cast<int>(r % Ho), n = static_cast<int>(r / Ho);
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v = (layout == CAI_LAYOUT_NHWC) ? x[((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c]
+                                        : x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + ix];
+      }
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// col2im gather for tiny Cout (last deconv, Cout = 3): cols fp32 [N*H*W, Npad] with n = (ky*ks+kx)*Cout + co
+// -> out fp32 NCHW or NHWC [N, Cout, Ho, Wo], out(oy, ox) = bias + sum over taps with (oy + pad - ky) % stride == 0
+__global__ void __launch_bounds__(256)
+col2im_kernel(const float *__restrict__ cols, const float *__restrict__ bias, int N, int Cout, int H, int W, int Ho,
+              int Wo, int ksz, int stride, int pad, int Npad, int out_layout, float clamp_lo, float clamp_hi,
+              float *__restrict__ out) {
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Cout;
+  const int64_t gs = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
+    int co, ox, oy, n;
+    if (out_layout == CAI_LAYOUT_NHWC) {
+      co = static_cast<int>(i % Cout);
+      int64_t r = i / Cout;
+      ox = static_cast<int>(r % Wo);
+      r /= Wo;
+      oy = static_cast<int>(r % Ho);
+      n = static_cast<int>(r / Ho);
+    } else {
+      ox = static_cast<int>(i % Wo);
+      int64_t r = i / Wo;
+      oy = static_cast<int>(r % Ho);
+      r /= Ho;
+      co = static_cast<int>(r % Cout);
+      n = static_cast<int>(r / Cout);
+    }
+    float acc = bias ? bias[co] : 0.f;
+    for (int ky = (oy + pad) % stride; ky < ksz; ky += stride) {
+      const int iy = (oy + pad - ky) / stride;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = (ox + pad) % stride; kx < ksz; kx += stride) {
+        const int ix = (ox + pad - kx) / stride;
+        if (ix < 0 || ix >= W) continue;
+        acc += cols[((static_cast<int64_t>(n) * H + iy) * W + ix) * Npad + (ky * ksz + kx) * Cout + co];
+      }
+    }
+    if (clamp_lo < clamp_hi) acc = fminf(fmaxf(acc, clamp_lo), clamp_hi);
+    out[i] = acc;
+  }
+}
+
+static int ew_grid2(const DeviceProps &dp, int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(dp.sm_count) * 32;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+}  // namespace cai
+
+using namespace cai;
+
+extern "C" {
+
+int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
+  CAI_CHECK_ARG(d != nullptr, "cai_conv_gemm: NULL descriptor");
+  CAI_CHECK_ARG(d->a_hi && d->a_lo && d->w_packed, "cai_conv_gemm: NULL operand");
+  CAI_CHECK_ARG(d->N >= 1 && d->H >= 1 && d->W >= 1 && d->Hp >= 1 && d->Wp >= 1, "cai_conv_gemm: bad geometry");
+  CAI_CHECK_ARG(d->Cin >= 8 && d->Cin % 8 == 0, "cai_conv_gemm: Cin=%d must be a multiple of 8", d->Cin);
+  CAI_CHECK_ARG(d->BN >= 16 && d->BN <= 256 && d->BN % 16 == 0, "cai_conv_gemm: BN=%d must be a multiple of 16 <= 256",
+                d->BN);
+  CAI_CHECK_ARG(d->Cout >= 16 && d->Cout % 16 == 0, "cai_conv_gemm: Cout=%d must be a multiple of 16", d->Cout);
+  CAI_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "cai_conv_gemm: ntaps=%d out of range", d->ntaps);
+  CAI_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= 4, "cai_conv_gemm: bad epilogue");
+  CAI_CHECK_ARG(d->epilogue < 3 || (d->aux_hi && d->aux_lo), "cai_conv_gemm: GDN epilogue needs aux planes");
+  CAI_CHECK_ARG(d->out_f32 || d->out_hi, "cai_conv_gemm: no output");
+  CAI_CHECK_ARG((d->out_hi == nullptr) == (d->out_lo == nullptr) && (d->sq_hi == nullptr) == (d->sq_lo == nullptr) &&
+                    (d->abs_hi == nullptr) == (d->abs_lo == nullptr),
+                "cai_conv_gemm: split planes come in pairs");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  ConvKernelParams p{};
+  p.a_hi = static_cast<const __nv_bfloat16 *>(d->a_hi);
+  p.a_lo = static_cast<const __nv_bfloat16 *>(d->a_lo);
+  p.w_packed = static_cast<const unsigned char *>(d->w_packed);
+  p.bias = d->bias;
+  p.aux_hi = static_cast<const __nv_bfloat16 *>(d->aux_hi);
+  p.aux_lo = static_cast<const __nv_bfloat16 *>(d->aux_lo);
+  p.out_f32 = d->out_f32;
+  p.out_hi = static_cast<__nv_bfloat16 *>(d->out_hi);
+  p.out_lo = static_cast<__nv_bfloat16 *>(d->out_lo);
+  p.sq_hi = static_cast<__nv_bfloat16 *>(d->sq_hi);
+  p.sq_lo = static_cast<__nv_bfloat16 *>(d->sq_lo);
+  p.abs_hi = static_cast<__nv_bfloat16 *>(d->abs_hi);
+  p.abs_lo = static_cast<__nv_bfloat16 *>(d->abs_lo);
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+  p.Hp = d->Hp; p.Wp = d->Wp; p.os = d->os; p.o0y = d->o0y; p.o0x = d->o0x; p.is = d->is;
+  p.ntaps = d->ntaps;
+  p.kchunks = (d->Cin + kBK - 1) / kBK;
+  p.BN = d->BN;
+  p.epilogue = d->epilogue;
+  p.clamp_lo = d->clamp_lo;
+  p.clamp_hi = d->clamp_hi;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.dy[t] = d->dy[t];
+    p.dx[t] = d->dx[t];
+  }
+  const size_t stage_bytes = 2 * (kBM * kBK * 2) + 2 * static_cast<size_t>(d->BN) * kBK * 2;
+  int stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes);
+  if (stages > 4) stages = 4;
+  const int ksteps = p.ntaps * p.kchunks;
+  if (stages > ksteps) stages = ksteps < 2 ? 2 : ksteps;
+  CAI_CHECK_ARG(stages >= 2, "cai_conv_gemm: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes;
+  const int64_t M_total = static_cast<int64_t>(d->N) * d->Hp * d->Wp;
+  const int64_t mt = (M_total + kBM - 1) / kBM;
+  const int nt = (d->Cout + d->BN - 1) / d->BN;
+  CAI_CHECK_ARG(mt <= 0x7fffffff && nt <= 65535, "cai_conv_gemm: grid too large");
+  CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  conv_gemm_kernel<<<dim3(static_cast<unsigned>(mt), static_cast<unsigned>(nt)), kConvThreads, smem,
+                     static_cast<cudaStream_t>(stream_)>>>(p);
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_split_planes(const float *x, int32_t layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad, void *hi, void *lo,
+                     cai_stream_t stream_) {
+  CAI_CHECK_ARG(x && hi && lo && Cpad >= C && N >= 0 && C >= 1 && HW >= 0, "cai_split_planes: bad arguments");
+  if (N * HW == 0) return CAI_OK;
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  split_planes_kernel<<<ew_grid2(dp, N * HW * Cpad), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      x, layout, N, C, HW, Cpad, static_cast<__nv_bfloat16 *>(hi), static_cast<__nv_bfloat16 *>(lo));
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                     int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad, void *hi, void *lo, cai_stream_t stream_) {
+  CAI_CHECK_ARG(x && hi && lo && Kpad >= ksize * ksize * C && Kpad % 8 == 0, "cai_im2col_split: bad arguments");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  im2col_split_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * Kpad), 256, 0,
+                        static_cast<cudaStream_t>(stream_)>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad,
+                                                              static_cast<__nv_bfloat16 *>(hi),
+                                                              static_cast<__nv_bfloat16 *>(lo));
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, int32_t H, int32_t W, int32_t Ho,
+               int32_t Wo, int32_t ksize, int32_t stride, int32_t pad, int32_t Npad, int32_t out_layout, float clamp_lo,
+               float clamp_hi, float *out, cai_stream_t stream_) {
+  CAI_CHECK_ARG(cols && out && Npad >= ksize * ksize * Cout, "cai_col2im: bad arguments");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  col2im_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * Cout), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      cols, bias, N, Cout, H, W, Ho, Wo, ksize, stride, pad, Npad, out_layout, clamp_lo, clamp_hi, out);
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+}  // extern "C"

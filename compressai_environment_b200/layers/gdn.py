@@ -28,6 +28,7 @@ class GDN(nn.Module):
         self.gamma_reparam = NonNegativeParametrizer()
         gamma = gamma_init * torch.eye(in_channels)
         self.gamma = nn.Parameter(self.gamma_reparam.init(gamma))
+        self._packed = None
 
     def effective_params(self):
         """(beta [C], gamma [C, C]) after the non-negative reparametrisation (tiny tensors)."""
@@ -36,5 +37,7 @@ class GDN(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         from .. import transforms
 
-        beta, gamma = self.effective_params()
-        return transforms.gdn(x, beta, gamma, self.inverse)
+        if torch.is_grad_enabled() and (x.requires_grad or self.beta.requires_grad):
+            beta, gamma = self.effective_params()
+            return transforms.gdn(x, beta, gamma, self.inverse)
+        return transforms.run_stack([self], x)

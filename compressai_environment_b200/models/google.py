@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from ..entropy_models import EntropyBottleneck, GaussianConditional
 from ..layers import GDN
+from ..transforms import TransformStack
 from .utils import conv, deconv, update_registered_buffers
 
 __all__ = [
@@ -75,8 +76,8 @@ class FactorizedPrior(CompressionModel):
 
     def __init__(self, N, M, **kwargs):
         super().__init__(entropy_bottleneck_channels=M, **kwargs)
-        self.g_a = nn.Sequential(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
-        self.g_s = nn.Sequential(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
+        self.g_a = TransformStack(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+        self.g_s = TransformStack(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
                                  deconv(N, N), GDN(N, inverse=True), deconv(N, 3))
         self.N = N
         self.M = M
@@ -126,12 +127,12 @@ class ScaleHyperprior(CompressionModel):
 
     def __init__(self, N, M, **kwargs):
         super().__init__(entropy_bottleneck_channels=N, **kwargs)
-        self.g_a = nn.Sequential(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
-        self.g_s = nn.Sequential(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
+        self.g_a = TransformStack(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+        self.g_s = TransformStack(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
                                  deconv(N, N), GDN(N, inverse=True), deconv(N, 3))
-        self.h_a = nn.Sequential(conv(M, N, stride=1, kernel_size=3), nn.ReLU(inplace=True), conv(N, N),
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.ReLU(inplace=True), conv(N, N),
                                  nn.ReLU(inplace=True), conv(N, N))
-        self.h_s = nn.Sequential(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N), nn.ReLU(inplace=True),
+        self.h_s = TransformStack(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N), nn.ReLU(inplace=True),
                                  conv(N, M, stride=1, kernel_size=3), nn.ReLU(inplace=True))
         self.gaussian_conditional = GaussianConditional(None)
         self.N = int(N)
@@ -217,9 +218,9 @@ class MeanScaleHyperprior(ScaleHyperprior):
 
     def __init__(self, N, M, **kwargs):
         super().__init__(N, M, **kwargs)
-        self.h_a = nn.Sequential(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True), conv(N, N),
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True), conv(N, N),
                                  nn.LeakyReLU(inplace=True), conv(N, N))
-        self.h_s = nn.Sequential(deconv(N, M), nn.LeakyReLU(inplace=True), deconv(M, M * 3 // 2),
+        self.h_s = TransformStack(deconv(N, M), nn.LeakyReLU(inplace=True), deconv(M, M * 3 // 2),
                                  nn.LeakyReLU(inplace=True), conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
 
     def _hyper_in(self, y):

@@ -1,22 +1,37 @@
-"""Analysis / synthesis transform building blocks: ``Conv2d``, ``ConvTranspose2d`` and ``gdn``.
+"""Analysis / synthesis transforms on the tcgen05 implicit-GEMM kernel (``cai_conv_gemm``).
 
 Reference: the ``conv`` / ``deconv`` factories (compressai/models/utils.py:128-146: k=5, s=2, pad=k//2,
-output_padding=s-1) build ``nn.Conv2d`` / ``nn.ConvTranspose2d``; GDN is compressai/layers/gdn.py:77-92.
-The modules here keep torch's parameter names and shapes (``weight`` [Cout, Cin, k, k] for conv,
-[Cin, Cout, k, k] for transposed conv, ``bias`` [Cout]) so reference checkpoints load unchanged.
-Activations are kept channels-last (NHWC) between layers: that is the layout the implicit-GEMM kernels
-read (K = Cin contiguous) and the fused quantize/index kernels transpose from.
+output_padding=s-1) build ``nn.Conv2d`` / ``nn.ConvTranspose2d``; GDN is compressai/layers/gdn.py:77-92;
+the stacks are compressai/models/google.py:134-152, :219-254, :339-353.  The modules here keep torch's
+parameter names and shapes (``weight`` [Cout, Cin, k, k] for conv, [Cin, Cout, k, k] for transposed conv,
+``bias`` [Cout]) so reference checkpoints load unchanged.
+
+Inference data flow (``run_stack``): activations travel between layers as *split planes* (two bf16 NHWC
+tensors hi + lo, see include/cai_b200.h) so that the A operand of the implicit GEMM is a pure cp.async copy;
+weights are split and tiled once per parameter version (``pack_weights``) into the UMMA canonical layout.
+  conv   -> one launch (one phase, k*k taps)
+  deconv -> stride^2 launches (one per output phase; 9/6/6/4 taps for k5 s2)
+  GDN    -> one launch: 1x1 GEMM of the x^2 planes with gamma, epilogue out = x * rsqrt(. + beta)
+  Cin=3 first layer  -> im2col to K=80 + 1x1 GEMM;  Cout=3 last layer -> 1x1 GEMM to N=80 + col2im gather
+ReLU / LeakyReLU / abs / clamp are folded into the producing launch's epilogue.
+
+Training (autograd) uses the same kernels for the forward of GDN/likelihoods; the convolution backward is not
+on the hot path named by BASELINE.json and is delegated to torch autograd (library call).
 """
 from __future__ import annotations
 
 import math
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
-from ._lib import require_cuda
+from . import _lib
+from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, ConvDesc, check, current_stream, lib, ptr, require_cuda
+
+_BK = 64
 
 
 class Conv2d(nn.Module):
@@ -28,6 +43,7 @@ class Conv2d(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels))
         self.reset_parameters()
+        self._packed = None
 
     def reset_parameters(self):  # same init as nn.Conv2d
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -36,7 +52,9 @@ class Conv2d(nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, x: Tensor) -> Tensor:
-        return conv2d(x, self.weight, self.bias, self.stride, self.padding)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return F.conv2d(x, self.weight, self.bias, stride=self.stride, padding=self.padding)
+        return run_stack([self], x)
 
     def extra_repr(self):
         return f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}"
@@ -52,6 +70,7 @@ class ConvTranspose2d(nn.Module):
         self.weight = nn.Parameter(torch.empty(in_channels, out_channels, kernel_size, kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels))
         self.reset_parameters()
+        self._packed = None
 
     def reset_parameters(self):  # same init as nn.ConvTranspose2d (fan_in computed on dim 1)
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -60,24 +79,364 @@ class ConvTranspose2d(nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, x: Tensor) -> Tensor:
-        return conv_transpose2d(x, self.weight, self.bias, self.stride, self.padding, self.output_padding)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return F.conv_transpose2d(x, self.weight, self.bias, stride=self.stride, padding=self.padding,
+                                      output_padding=self.output_padding)
+        return run_stack([self], x)
 
     def extra_repr(self):
         return f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}"
 
 
-# ---- compute entry points (single dispatch point for the transform kernels) ---------------------------------
-def conv2d(x, weight, bias, stride, padding):
-    require_cuda(x, "inputs")
-    return F.conv2d(x, weight, bias, stride=stride, padding=padding)
+class TransformStack(nn.Sequential):
+    """``nn.Sequential`` whose inference forward runs the whole stack on the fused kernels (same submodule
+    names / state_dict keys as the reference's plain Sequential)."""
+
+    def forward(self, x, **kw):
+        if torch.is_grad_enabled() and (getattr(x, "requires_grad", False) or any(p.requires_grad for p in self.parameters())):
+            for m in self:
+                x = m(x)
+            return x
+        return run_stack(list(self), x, **kw)
 
 
-def conv_transpose2d(x, weight, bias, stride, padding, output_padding):
+# ---- split planes ---------------------------------------------------------------------------------------------
+class Planes:
+    """fp32 NHWC activation stored as two bf16 NHWC tensors (hi + lo)."""
+
+    __slots__ = ("hi", "lo", "N", "H", "W", "C")
+
+    def __init__(self, hi, lo, N, H, W, C):
+        self.hi, self.lo, self.N, self.H, self.W, self.C = hi, lo, N, H, W, C
+
+    @staticmethod
+    def empty(N, H, W, C, device):
+        return Planes(torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device),
+                      torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device), N, H, W, C)
+
+
+def to_planes(x: Tensor, c_pad: Optional[int] = None) -> Planes:
     require_cuda(x, "inputs")
-    return F.conv_transpose2d(x, weight, bias, stride=stride, padding=padding, output_padding=output_padding)
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    N, C, H, W = x.shape
+    if x.is_contiguous():
+        layout = CAI_LAYOUT_NCHW
+    elif x.is_contiguous(memory_format=torch.channels_last):
+        layout = CAI_LAYOUT_NHWC
+    else:
+        x, layout = x.contiguous(), CAI_LAYOUT_NCHW
+    Cp = C if c_pad is None else c_pad
+    out = Planes.empty(N, H, W, Cp, x.device)
+    with torch.cuda.device(x.device):
+        check(lib().cai_split_planes(ptr(x), layout, N, C, H * W, Cp, ptr(out.hi), ptr(out.lo), current_stream()),
+              "cai_split_planes")
+    return out
+
+
+# ---- weight packing -------------------------------------------------------------------------------------------
+def _choose_bn(cout: int) -> int:
+    if cout <= 256:
+        return cout
+    for parts in range(2, 64):
+        if cout % parts == 0 and (cout // parts) % 16 == 0 and cout // parts <= 256:
+            return cout // parts
+    return 128
+
+
+def pack_weights(w_taps: Tensor, bn: int) -> Tensor:
+    """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][T * kchunks][hi | lo][BN x 64 bf16] in the UMMA canonical
+    K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2)."""
+    T, cout, cin = w_taps.shape
+    nt = (cout + bn - 1) // bn
+    kc = (cin + _BK - 1) // _BK
+    wp = torch.zeros((T, nt * bn, kc * _BK), dtype=torch.float32, device=w_taps.device)
+    wp[:, :cout, :cin] = w_taps
+    wp = wp.view(T, nt, bn // 8, 8, kc, 8, 8).permute(1, 0, 4, 5, 2, 3, 6)  # nt, T, kc, k8, r8, r%8, k%8
+    hi = wp.to(torch.bfloat16)
+    lo = (wp - hi.float()).to(torch.bfloat16)
+    packed = torch.stack([hi, lo], dim=3).contiguous()  # nt, T, kc, 2, k8, r8, r%8, k%8
+    return packed.view(torch.uint8).reshape(-1)
+
+
+class _Layer:
+    """One GEMM launch family prepared from a module (cached on the module, keyed by parameter versions)."""
+
+    def __init__(self, kind, packed, bias, taps_per_phase, bn, cin, cout, geom):
+        self.kind, self.packed, self.bias, self.phases, self.bn = kind, packed, bias, taps_per_phase, bn
+        self.cin, self.cout, self.geom = cin, cout, geom
+
+
+def _param_key(*ps):
+    return tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+
+
+def _prep_conv(m: "Conv2d") -> _Layer:
+    key = _param_key(m.weight, m.bias)
+    if m._packed is not None and m._packed[0] == key:
+        return m._packed[1]
+    k, s, p = m.kernel_size, m.stride, m.padding
+    w = m.weight.detach().float()
+    cout, cin = w.shape[0], w.shape[1]
+    if cin < 16:  # im2col path: one 1x1 GEMM over K = k*k*cin (padded to a multiple of 8)
+        kflat = k * k * cin
+        kpad = (kflat + 15) // 16 * 16
+        wt = w.permute(0, 2, 3, 1).reshape(1, cout, kflat)  # k index = (ky*k + kx)*cin + ci
+        bn = _choose_bn(cout)
+        lay = _Layer("conv_im2col", pack_weights(wt, bn), m.bias.detach().float().contiguous(), [[(0, 0)]], bn, kpad,
+                     cout, (k, s, p, kpad))
+    else:
+        wt = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+        taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
+        bn = _choose_bn(cout)
+        lay = _Layer("conv", pack_weights(wt, bn), m.bias.detach().float().contiguous(), [taps], bn, cin, cout, (k, s, p))
+    m._packed = (key, lay)
+    return lay
+
+
+def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
+    key = _param_key(m.weight, m.bias)
+    if m._packed is not None and m._packed[0] == key:
+        return m._packed[1]
+    k, s, p, op = m.kernel_size, m.stride, m.padding, m.output_padding
+    w = m.weight.detach().float()
+    cin, cout = w.shape[0], w.shape[1]
+    if cout < 16:  # col2im path: 1x1 GEMM to N = k*k*cout columns, then a gather
+        nflat = k * k * cout
+        npad = (nflat + 15) // 16 * 16
+        wt = w.permute(2, 3, 1, 0).reshape(1, nflat, cin)  # row index = (ky*k + kx)*cout + co
+        lay = _Layer("deconv_col2im", pack_weights(wt, npad), m.bias.detach().float().contiguous(), [[(0, 0)]], npad,
+                     cin, cout, (k, s, p, op, npad))
+    else:
+        bn = _choose_bn(cout)
+        phases, blobs = [], []
+        for py in range(s):
+            for px in range(s):
+                taps, ws = [], []
+                for ky in range(k):
+                    if (py + p - ky) % s:
+                        continue
+                    for kx in range(k):
+                        if (px + p - kx) % s:
+                            continue
+                        taps.append(((py + p - ky) // s, (px + p - kx) // s))
+                        ws.append(w[:, :, ky, kx].t())  # [cout, cin]
+                phases.append(taps)
+                blobs.append(pack_weights(torch.stack(ws, 0), bn) if ws else None)
+        lay = _Layer("deconv", blobs, m.bias.detach().float().contiguous(), phases, bn, cin, cout, (k, s, p, op))
+    m._packed = (key, lay)
+    return lay
+
+
+def _prep_gdn(m) -> _Layer:
+    key = _param_key(m.beta, m.gamma)
+    cached = getattr(m, "_packed", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    with torch.no_grad():
+        beta, gamma = m.effective_params()
+    C = gamma.shape[0]
+    bn = _choose_bn(C)
+    lay = _Layer("igdn" if m.inverse else "gdn", pack_weights(gamma.detach().float().reshape(1, C, C), bn),
+                 beta.detach().float().contiguous(), [[(0, 0)]], bn, C, C, None)
+    m._packed = (key, lay)
+    return lay
+
+
+# ---- launches -------------------------------------------------------------------------------------------------
+def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o0x, is_, epilogue=0, aux: Planes = None,
+            out_f32=None, out: Planes = None, sq: Planes = None, ab: Planes = None, clamp=None):
+    d = ConvDesc()
+    d.a_hi, d.a_lo, d.w_packed = a.hi.data_ptr(), a.lo.data_ptr(), packed.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    if aux is not None:
+        d.aux_hi, d.aux_lo = aux.hi.data_ptr(), aux.lo.data_ptr()
+    if out_f32 is not None:
+        d.out_f32 = out_f32.data_ptr()
+    if out is not None:
+        d.out_hi, d.out_lo = out.hi.data_ptr(), out.lo.data_ptr()
+    if sq is not None:
+        d.sq_hi, d.sq_lo = sq.hi.data_ptr(), sq.lo.data_ptr()
+    if ab is not None:
+        d.abs_hi, d.abs_lo = ab.hi.data_ptr(), ab.lo.data_ptr()
+    d.N, d.H, d.W, d.Cin, d.Ho, d.Wo, d.Cout = a.N, a.H, a.W, a.C, Ho, Wo, cout
+    d.Hp, d.Wp, d.os, d.o0y, d.o0x, d.is_ = Hp, Wp, os_, o0y, o0x, is_
+    d.ntaps, d.BN, d.epilogue = len(taps), bn, epilogue
+    d.clamp_lo, d.clamp_hi = (clamp if clamp is not None else (0.0, 0.0))
+    for t, (dy, dx) in enumerate(taps):
+        d.dy[t], d.dx[t] = dy, dx
+    with torch.cuda.device(a.hi.device):
+        check(lib().cai_conv_gemm(d, current_stream()), "cai_conv_gemm")
+
+
+_ACT = {None: 0, "relu": 1, "leaky": 2}
+
+
+def _outputs(N, Ho, Wo, C, device, want):
+    out_f32 = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=device) if "f32" in want else None
+    out = Planes.empty(N, Ho, Wo, C, device) if "planes" in want else None
+    sq = Planes.empty(N, Ho, Wo, C, device) if "sq" in want else None
+    ab = Planes.empty(N, Ho, Wo, C, device) if "abs" in want else None
+    return out_f32, out, sq, ab
+
+
+def _run_conv(m, x, act, want, clamp=None):
+    """x: Planes (or fp32 tensor for the im2col first layer). Returns (f32 NHWC tensor | None, planes, sq, abs)."""
+    lay = _prep_conv(m)
+    dev = m.weight.device
+    if lay.kind == "conv_im2col":
+        k, s, p, kpad = lay.geom
+        if isinstance(x, Planes):
+            raise _lib.CaiError("a conv with fewer than 16 input channels must be the first layer of a stack")
+        xt = x.detach().float()
+        N, C, H, W = xt.shape
+        layout = CAI_LAYOUT_NCHW
+        if not xt.is_contiguous():
+            if xt.is_contiguous(memory_format=torch.channels_last):
+                layout = CAI_LAYOUT_NHWC
+            else:
+                xt = xt.contiguous()
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        a = Planes.empty(N, Ho, Wo, kpad, dev)
+        with torch.cuda.device(dev):
+            check(lib().cai_im2col_split(ptr(xt), layout, N, C, H, W, Ho, Wo, k, s, p, kpad, ptr(a.hi), ptr(a.lo),
+                                         current_stream()), "cai_im2col_split")
+        o = _outputs(N, Ho, Wo, lay.cout, dev, want)
+        _launch(a, lay.packed, lay.bias, [(0, 0)], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, 1, _ACT[act], None, *o,
+                clamp=clamp)
+        return o
+    if not isinstance(x, Planes):
+        x = to_planes(x)
+    k, s, p = lay.geom
+    Ho, Wo = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+    o = _outputs(x.N, Ho, Wo, lay.cout, dev, want)
+    _launch(x, lay.packed, lay.bias, lay.phases[0], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, s, _ACT[act], None, *o,
+            clamp=clamp)
+    return o
+
+
+def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False):
+    lay = _prep_deconv(m)
+    dev = m.weight.device
+    if not isinstance(x, Planes):
+        x = to_planes(x)
+    if lay.kind == "deconv_col2im":
+        k, s, p, op, npad = lay.geom
+        Ho, Wo = (x.H - 1) * s - 2 * p + k + op, (x.W - 1) * s - 2 * p + k + op
+        cols = torch.empty((x.N, x.H, x.W, npad), dtype=torch.float32, device=dev)
+        _launch(x, lay.packed, None, [(0, 0)], lay.bn, npad, x.H, x.W, x.H, x.W, 1, 0, 0, 1, 0, None, cols, None, None,
+                None)
+        if final_layout_nchw:
+            out = torch.empty((x.N, lay.cout, Ho, Wo), dtype=torch.float32, device=dev)
+            layout = CAI_LAYOUT_NCHW
+        else:
+            out = torch.empty((x.N, Ho, Wo, lay.cout), dtype=torch.float32, device=dev)
+            layout = CAI_LAYOUT_NHWC
+        lo, hi = clamp if clamp is not None else (0.0, 0.0)
+        with torch.cuda.device(dev):
+            check(lib().cai_col2im(ptr(cols), ptr(lay.bias), x.N, lay.cout, x.H, x.W, Ho, Wo, k, s, p, npad, layout, lo,
+                                   hi, ptr(out), current_stream()), "cai_col2im")
+        if act == "relu":
+            out.clamp_(min=0)
+        return out, None, None, None
+    k, s, p, op = lay.geom
+    Ho, Wo = (x.H - 1) * s - 2 * p + k + op, (x.W - 1) * s - 2 * p + k + op
+    o = _outputs(x.N, Ho, Wo, lay.cout, dev, want)
+    i = 0
+    for py in range(s):
+        for px in range(s):
+            taps, blob = lay.phases[i], lay.packed[i]
+            i += 1
+            Hp, Wp = (Ho - py + s - 1) // s, (Wo - px + s - 1) // s
+            if Hp <= 0 or Wp <= 0:
+                continue
+            if not taps:
+                raise _lib.CaiError("transposed convolution phase without taps is not supported (kernel < stride)")
+            _launch(x, blob, lay.bias, taps, lay.bn, lay.cout, Ho, Wo, Hp, Wp, s, py, px, 1, _ACT[act], None, *o,
+                    clamp=clamp)
+    return o
+
+
+def _run_gdn(m, x: Planes, sq: Planes, want):
+    lay = _prep_gdn(m)
+    o = _outputs(x.N, x.H, x.W, lay.cout, x.hi.device, want)
+    _launch(sq, lay.packed, lay.bias, [(0, 0)], lay.bn, lay.cout, x.H, x.W, x.H, x.W, 1, 0, 0, 1,
+            4 if lay.kind == "igdn" else 3, x, *o)
+    return o
+
+
+def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw_out: bool = False):
+    """Run a conv / GDN / activation stack on the fused kernels (inference).  ``x`` is an fp32 tensor (logical
+    NCHW, any memory format) or ``Planes``.  Returns the fp32 output as a logical-NCHW tensor stored channels-last
+    (or true NCHW when the last layer is the 3-channel col2im with ``nchw_out``); with ``want_abs`` also returns
+    the split planes of |output| for the following hyper-analysis stack."""
+    from .layers.gdn import GDN
+
+    i, n = 0, len(mods)
+    cur = x
+    result = None
+    is_nchw = False
+    while i < n:
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < n else None
+        if isinstance(m, (Conv2d, ConvTranspose2d)):
+            act = None
+            consumed = 1
+            if isinstance(nxt, nn.ReLU):
+                act, consumed = "relu", 2
+            elif isinstance(nxt, nn.LeakyReLU):
+                act, consumed = "leaky", 2
+            after = mods[i + consumed] if i + consumed < n else None
+            last = after is None
+            if isinstance(after, GDN):
+                want = ("planes", "sq")
+            elif last:
+                want = ("f32", "abs") if want_abs else ("f32",)
+            else:
+                want = ("planes",)
+            if isinstance(m, Conv2d):
+                o = _run_conv(m, cur, act, want, clamp if last else None)
+            else:
+                o = _run_deconv(m, cur, act, want, clamp if last else None, final_layout_nchw=nchw_out and last)
+                is_nchw = bool(nchw_out and last and m.out_channels < 16)
+            i += consumed
+            if isinstance(after, GDN):
+                glast = i + 1 >= n
+                go = _run_gdn(after, o[1], o[2], ("f32",) if glast else ("planes",))
+                i += 1
+                if glast:
+                    result = (go[0], None)
+                else:
+                    cur = go[1]
+            elif last:
+                result = (o[0], o[3])
+            else:
+                cur = o[1]
+        elif isinstance(m, GDN):
+            # GDN not preceded by a conv of this stack: build its operands from the fp32 input
+            xt = cur if not isinstance(cur, Planes) else None
+            if xt is None:
+                raise _lib.CaiError("standalone GDN needs an fp32 tensor input")
+            xp = to_planes(xt)
+            sq = to_planes(xt.detach().float() ** 2)
+            glast = i + 1 >= n
+            go = _run_gdn(m, xp, sq, ("f32",) if glast else ("planes",))
+            i += 1
+            if glast:
+                result = (go[0], None)
+            else:
+                cur = go[1]
+        else:
+            raise _lib.CaiError(f"run_stack: unsupported module {type(m).__name__}")
+    out, ab = result
+    if not is_nchw:
+        out = out.permute(0, 3, 1, 2)  # NHWC storage -> logical NCHW (channels_last strides)
+    return (out, ab) if want_abs else out
 
 
 def gdn(x, beta, gamma, inverse):
+    """Functional GDN used by ``layers.GDN.forward`` in training mode (autograd through torch ops)."""
     require_cuda(x, "inputs")
     C = x.size(1)
     norm = F.conv2d(x * x, gamma.reshape(C, C, 1, 1), beta)

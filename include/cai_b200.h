@@ -215,6 +215,56 @@ int cai_eb_backward(const float *x_tilde, const float *tparams, const int32_t *f
 int cai_eb_logits(const float *x, const float *tparams, const int32_t *filters_host, int32_t n_filters,
                   const float *g_out, int64_t C, int64_t L, float *out, float *g_x, cai_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Transforms: tcgen05 implicit-GEMM convolution / transposed convolution / GDN.
+ * Replaces the cuDNN / ATen kernels behind compressai/models/utils.py:128-146 (conv, deconv),
+ * compressai/layers/gdn.py:77-92 (GDN / IGDN) as used by the g_a / g_s / h_a / h_s stacks of
+ * compressai/models/google.py:134-152, :219-254, :339-353.
+ *
+ * Activations are "split planes": an fp32 NHWC tensor stored as two bf16 NHWC tensors hi = bf16(x),
+ * lo = bf16(x - hi) (same bytes as fp32; x ~= hi + lo to 2^-17 relative).  One call computes, for one
+ * output phase grid of Hp x Wp pixels per image,
+ *     D[pixel, co] = sum_{t < ntaps} sum_{ci} A[n, i*is + dy[t], j*is + dx[t], ci] * Wt[co, t, ci]
+ * (out-of-range input pixels read as zero) and writes pixel (i*os + o0y, j*os + o0x) of the output.
+ * w_packed holds the weights pre-split and pre-tiled by the host layer (see transforms.py:pack_weights):
+ * [n_tile][kstep = t * kchunks + kc][hi | lo][BN x 64 bf16 in UMMA canonical K-major order].
+ * epilogue: 0 linear, 1 ReLU, 2 LeakyReLU(0.01), 3 GDN  out = aux * rsqrt(D + bias),
+ *           4 IGDN out = aux * sqrt(D + bias)   (aux given as split planes shaped like the output).
+ * Outputs (any subset): out_f32 fp32 NHWC, out_hi/lo split planes, sq_hi/lo planes of out^2 (the GDN
+ * input), abs_hi/lo planes of |out| (the hyper-analysis input of ScaleHyperprior).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cai_conv_desc {
+  const void *a_hi, *a_lo;   /* bf16 [N, H, W, Cin] */
+  const void *w_packed;
+  const float *bias;         /* [Cout] or NULL */
+  const void *aux_hi, *aux_lo;
+  float *out_f32;
+  void *out_hi, *out_lo, *sq_hi, *sq_lo, *abs_hi, *abs_lo;
+  int32_t N, H, W, Cin, Ho, Wo, Cout;
+  int32_t Hp, Wp, os, o0y, o0x, is;
+  int32_t ntaps;
+  int32_t BN;                /* output channels per tile: multiple of 16, <= 256 */
+  int32_t epilogue;
+  float clamp_lo, clamp_hi;  /* clamp applied when clamp_lo < clamp_hi */
+  int8_t dy[32], dx[32];
+} cai_conv_desc;
+
+int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream);
+
+/* fp32 latent / image (layout NCHW or NHWC) -> split planes [N, HW, Cpad] (channels zero padded to Cpad) */
+int cai_split_planes(const float *x, int32_t layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad, void *hi, void *lo,
+                     cai_stream_t stream);
+
+/* im2col for tiny Cin (the 3-channel first layer): split planes [N*Ho*Wo, Kpad], k = (ky*ksize + kx)*C + c */
+int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                     int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad, void *hi, void *lo, cai_stream_t stream);
+
+/* col2im gather for tiny Cout (the 3-channel last layer of g_s): cols fp32 [N*H*W, Npad] with
+ * column (ky*ksize + kx)*Cout + co  ->  out fp32 [N, Cout, Ho, Wo] (out_layout NCHW) or NHWC, + bias, optional clamp */
+int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, int32_t H, int32_t W, int32_t Ho,
+               int32_t Wo, int32_t ksize, int32_t stride, int32_t pad, int32_t Npad, int32_t out_layout, float clamp_lo,
+               float clamp_hi, float *out, cai_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
