@@ -136,6 +136,29 @@ def to_planes(x: Tensor, c_pad: Optional[int] = None) -> Planes:
 
 
 # ---- weight packing -------------------------------------------------------------------------------------------
+def _c16(c: int) -> int:
+    """Channel counts are padded to a multiple of 16 (UMMA N granularity at M = 128; K chunks of 8)."""
+    return (int(c) + 15) // 16 * 16
+
+
+def _pad_taps(wt: Tensor, cout_p: int, cin_p: int) -> Tensor:
+    T, cout, cin = wt.shape
+    if cout == cout_p and cin == cin_p:
+        return wt
+    out = torch.zeros((T, cout_p, cin_p), dtype=wt.dtype, device=wt.device)
+    out[:, :cout, :cin] = wt
+    return out
+
+
+def _pad_vec(v: Tensor, n: int, fill: float = 0.0) -> Tensor:
+    v = v.detach().float().reshape(-1)
+    if v.numel() == n:
+        return v.contiguous()
+    out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
+    out[:v.numel()] = v
+    return out
+
+
 def _choose_bn(cout: int) -> int:
     if cout <= 256:
         return cout
@@ -179,18 +202,20 @@ def _prep_conv(m: "Conv2d") -> _Layer:
     k, s, p = m.kernel_size, m.stride, m.padding
     w = m.weight.detach().float()
     cout, cin = w.shape[0], w.shape[1]
-    if cin < 16:  # im2col path: one 1x1 GEMM over K = k*k*cin (padded to a multiple of 8)
+    if cin <= 4:  # im2col path: one 1x1 GEMM over K = k*k*cin (padded to a multiple of 8)
         kflat = k * k * cin
         kpad = (kflat + 15) // 16 * 16
         wt = w.permute(0, 2, 3, 1).reshape(1, cout, kflat)  # k index = (ky*k + kx)*cin + ci
-        bn = _choose_bn(cout)
-        lay = _Layer("conv_im2col", pack_weights(wt, bn), m.bias.detach().float().contiguous(), [[(0, 0)]], bn, kpad,
-                     cout, (k, s, p, kpad))
+        cp = _c16(cout)
+        bn = _choose_bn(cp)
+        lay = _Layer("conv_im2col", pack_weights(_pad_taps(wt, cp, kflat), bn), _pad_vec(m.bias, cp), [[(0, 0)]], bn,
+                     kpad, cp, (k, s, p, kpad))
     else:
         wt = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
         taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
-        bn = _choose_bn(cout)
-        lay = _Layer("conv", pack_weights(wt, bn), m.bias.detach().float().contiguous(), [taps], bn, cin, cout, (k, s, p))
+        cp, kp = _c16(cout), _c16(cin)
+        bn = _choose_bn(cp)
+        lay = _Layer("conv", pack_weights(_pad_taps(wt, cp, kp), bn), _pad_vec(m.bias, cp), [taps], bn, kp, cp, (k, s, p))
     m._packed = (key, lay)
     return lay
 
@@ -202,14 +227,15 @@ def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
     k, s, p, op = m.kernel_size, m.stride, m.padding, m.output_padding
     w = m.weight.detach().float()
     cin, cout = w.shape[0], w.shape[1]
-    if cout < 16:  # col2im path: 1x1 GEMM to N = k*k*cout columns, then a gather
+    if cout <= 4:  # col2im path: 1x1 GEMM to N = k*k*cout columns, then a gather
         nflat = k * k * cout
         npad = (nflat + 15) // 16 * 16
         wt = w.permute(2, 3, 1, 0).reshape(1, nflat, cin)  # row index = (ky*k + kx)*cout + co
-        lay = _Layer("deconv_col2im", pack_weights(wt, npad), m.bias.detach().float().contiguous(), [[(0, 0)]], npad,
-                     cin, cout, (k, s, p, op, npad))
+        lay = _Layer("deconv_col2im", pack_weights(_pad_taps(wt, npad, _c16(cin)), npad),
+                     m.bias.detach().float().contiguous(), [[(0, 0)]], npad, _c16(cin), cout, (k, s, p, op, npad))
     else:
-        bn = _choose_bn(cout)
+        cp, kp = _c16(cout), _c16(cin)
+        bn = _choose_bn(cp)
         phases, blobs = [], []
         for py in range(s):
             for px in range(s):
@@ -223,8 +249,8 @@ def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
                         taps.append(((py + p - ky) // s, (px + p - kx) // s))
                         ws.append(w[:, :, ky, kx].t())  # [cout, cin]
                 phases.append(taps)
-                blobs.append(pack_weights(torch.stack(ws, 0), bn) if ws else None)
-        lay = _Layer("deconv", blobs, m.bias.detach().float().contiguous(), phases, bn, cin, cout, (k, s, p, op))
+                blobs.append(pack_weights(_pad_taps(torch.stack(ws, 0), cp, kp), bn) if ws else None)
+        lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op))
     m._packed = (key, lay)
     return lay
 
@@ -237,9 +263,11 @@ def _prep_gdn(m) -> _Layer:
     with torch.no_grad():
         beta, gamma = m.effective_params()
     C = gamma.shape[0]
-    bn = _choose_bn(C)
-    lay = _Layer("igdn" if m.inverse else "gdn", pack_weights(gamma.detach().float().reshape(1, C, C), bn),
-                 beta.detach().float().contiguous(), [[(0, 0)]], bn, C, C, None)
+    cp = _c16(C)
+    bn = _choose_bn(cp)
+    # padded channels: gamma = 0, beta = 1 -> out = 0 * rsqrt(1) = 0
+    lay = _Layer("igdn" if m.inverse else "gdn", pack_weights(_pad_taps(gamma.detach().float().reshape(1, C, C), cp, cp), bn),
+                 _pad_vec(beta, cp, 1.0), [[(0, 0)]], bn, cp, cp, None)
     m._packed = (key, lay)
     return lay
 
@@ -288,7 +316,7 @@ def _run_conv(m, x, act, want, clamp=None):
     if lay.kind == "conv_im2col":
         k, s, p, kpad = lay.geom
         if isinstance(x, Planes):
-            raise _lib.CaiError("a conv with fewer than 16 input channels must be the first layer of a stack")
+            raise _lib.CaiError("a conv with at most 4 input channels must be the first layer of a stack")
         xt = x.detach().float()
         N, C, H, W = xt.shape
         layout = CAI_LAYOUT_NCHW
@@ -307,7 +335,7 @@ def _run_conv(m, x, act, want, clamp=None):
                 clamp=clamp)
         return o
     if not isinstance(x, Planes):
-        x = to_planes(x)
+        x = to_planes(x, lay.cin)
     k, s, p = lay.geom
     Ho, Wo = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
     o = _outputs(x.N, Ho, Wo, lay.cout, dev, want)
@@ -320,7 +348,7 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False):
     lay = _prep_deconv(m)
     dev = m.weight.device
     if not isinstance(x, Planes):
-        x = to_planes(x)
+        x = to_planes(x, lay.cin)
     if lay.kind == "deconv_col2im":
         k, s, p, op, npad = lay.geom
         Ho, Wo = (x.H - 1) * s - 2 * p + k + op, (x.W - 1) * s - 2 * p + k + op
@@ -399,7 +427,7 @@ def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw
                 o = _run_conv(m, cur, act, want, clamp if last else None)
             else:
                 o = _run_deconv(m, cur, act, want, clamp if last else None, final_layout_nchw=nchw_out and last)
-                is_nchw = bool(nchw_out and last and m.out_channels < 16)
+                is_nchw = bool(nchw_out and last and m.out_channels <= 4)
             i += consumed
             if isinstance(after, GDN):
                 glast = i + 1 >= n
@@ -418,8 +446,9 @@ def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw
             xt = cur if not isinstance(cur, Planes) else None
             if xt is None:
                 raise _lib.CaiError("standalone GDN needs an fp32 tensor input")
-            xp = to_planes(xt)
-            sq = to_planes(xt.detach().float() ** 2)
+            cpad = _c16(xt.size(1))
+            xp = to_planes(xt, cpad)
+            sq = to_planes(xt.detach().float() ** 2, cpad)
             glast = i + 1 >= n
             go = _run_gdn(m, xp, sq, ("f32",) if glast else ("planes",))
             i += 1
@@ -432,7 +461,21 @@ def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw
     out, ab = result
     if not is_nchw:
         out = out.permute(0, 3, 1, 2)  # NHWC storage -> logical NCHW (channels_last strides)
+        true_c = _true_out_channels(mods)
+        if true_c is not None and true_c != out.size(1):
+            out = out[:, :true_c]  # drop the zero channels added to reach the tensor-core granularity
     return (out, ab) if want_abs else out
+
+
+def _true_out_channels(mods):
+    from .layers.gdn import GDN
+
+    for m in reversed(mods):
+        if isinstance(m, (Conv2d, ConvTranspose2d)):
+            return m.out_channels
+        if isinstance(m, GDN):
+            return int(m.beta.numel())
+    return None
 
 
 def gdn(x, beta, gamma, inverse):

@@ -80,7 +80,7 @@ def test_gdn_golden(golden):
         with torch.no_grad():
             m.beta.copy_(torch.from_numpy(f[tag + "_beta"]))
             m.gamma.copy_(torch.from_numpy(f[tag + "_gamma"]))
-            # C = 8 is below the tensor-core tile granularity: pad channels to 16 through a wider layer
+            # also exercise explicit zero-padding to 16 channels through a wider layer
             m16 = GDN(16, inverse=inv).to(DEV)
             m16.beta[:8] = m.beta
             m16.gamma.fill_(m16.gamma_reparam.init(torch.zeros(1, device=DEV)).item())
@@ -89,6 +89,22 @@ def test_gdn_golden(golden):
             x[:, :8] = torch.from_numpy(f[tag + "_x"]).to(DEV)
             y = m16(x)[:, :8]
         _check(y, torch.from_numpy(f[tag + "_y"]).to(DEV))
+        with torch.no_grad():
+            _check(m(torch.from_numpy(f[tag + "_x"]).to(DEV)), torch.from_numpy(f[tag + "_y"]).to(DEV))
+
+
+def test_odd_channel_counts():
+    """Channel counts that are not multiples of 16 are zero padded by the host layer."""
+    from compressai_environment_b200.transforms import Conv2d, ConvTranspose2d, run_stack
+
+    torch.manual_seed(5)
+    c1, c2, d1 = Conv2d(3, 8).to(DEV), Conv2d(8, 12).to(DEV), ConvTranspose2d(12, 8).to(DEV)
+    x = torch.rand(2, 3, 32, 48, device=DEV)
+    with torch.no_grad():
+        ref = F.conv2d(F.relu(F.conv2d(x, c1.weight, c1.bias, stride=2, padding=2)), c2.weight, c2.bias, stride=2, padding=2)
+        got = run_stack([c1, torch.nn.ReLU(), c2], x)
+        _check(got, ref)
+        _check(run_stack([d1], ref), F.conv_transpose2d(ref, d1.weight, d1.bias, stride=2, padding=2, output_padding=1))
 
 
 def test_full_stack_matches_torch():
