@@ -11,6 +11,10 @@ import os
 import subprocess
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int8, c_int32, c_int64, c_void_p
 
+# The codec pipeline runs ~10 streams (analysis, synthesis, one coder stream per in-flight chunk); with the default
+# of 8 hardware queues unrelated streams would alias and serialise.  Only effective before CUDA is initialised.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcai_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")

@@ -91,25 +91,30 @@ struct TableView {
 
 // ---- encoder -------------------------------------------------------------------------------------------
 struct EncEmit {
-  uint32_t *slot_end;  // one past the last word of this string's slot
-  int64_t cap;
-  int64_t cnt;
+  uint32_t *lane_ptr;  // slot_end - 1 - lane : word k (k = 32 * g + lane) goes to lane_ptr[-32 * g]
+  uint32_t cap;        // slot capacity in words (< 2^31)
+  uint32_t cnt;        // words emitted so far
   uint32_t buf;
-  int lane;
+  uint32_t lane;
+  __device__ __forceinline__ void flush_full() {  // cnt is a non-zero multiple of 32
+    const uint32_t k0 = cnt - 32u;
+    if (k0 + lane < cap) *(lane_ptr - static_cast<int64_t>(k0)) = buf;
+  }
   __device__ __forceinline__ void push(uint32_t w) {
-    if ((static_cast<int>(cnt) & 31) == lane) buf = w;
+    if ((cnt & 31u) == lane) buf = w;
     cnt += 1;
-    if ((cnt & 31) == 0) {
-      const int64_t k = cnt - 32 + lane;
-      if (k < cap) slot_end[-1 - k] = buf;
-    }
+    if ((cnt & 31u) == 0) flush_full();
+  }
+  // predicated variant for the hot path: no branch unless a 128-byte line completes
+  __device__ __forceinline__ void push_if(bool on, uint32_t w) {
+    buf = (on && (cnt & 31u) == lane) ? w : buf;
+    cnt += on ? 1u : 0u;
+    if (on && (cnt & 31u) == 0) flush_full();
   }
   __device__ __forceinline__ void finish() {
-    const int rem = static_cast<int>(cnt & 31);
-    if (lane < rem) {
-      const int64_t k = (cnt - rem) + lane;
-      if (k < cap) slot_end[-1 - k] = buf;
-    }
+    const uint32_t rem = cnt & 31u;
+    const uint32_t k0 = cnt - rem;
+    if (lane < rem && k0 + lane < cap) *(lane_ptr - static_cast<int64_t>(k0)) = buf;
   }
 };
 
@@ -149,11 +154,11 @@ rans_encode_kernel(const unsigned char *__restrict__ blob, uint32_t enc_bytes, c
     int32_t st = CAI_S_OK;
 
     EncEmit em;
-    em.slot_end = slots + (b + 1) * slot_words;
-    em.cap = slot_words;
+    em.lane_ptr = slots + (b + 1) * slot_words - 1 - lane;
+    em.cap = static_cast<uint32_t>(slot_words);
     em.cnt = 0;
     em.buf = 0;
-    em.lane = lane;
+    em.lane = static_cast<uint32_t>(lane);
 
     uint64_t x = 1ull << 31;
     const int64_t nchunks = (n + 31) >> 5;
@@ -239,30 +244,39 @@ rans_encode_kernel(const unsigned char *__restrict__ blob, uint32_t enc_bytes, c
       }
       const int64_t rem = n - (j << 5);
       const int nvalid = rem < 32 ? static_cast<int>(rem) : 32;
+      uint4 e_next = *reinterpret_cast<const uint4 *>(pp + (nvalid - 1));
 #pragma unroll 4
       for (int l = nvalid - 1; l >= 0; --l) {
-        const uint4 e = *reinterpret_cast<const uint4 *>(pp + l);
+        const uint4 e = e_next;
+        if (l > 0) e_next = *reinterpret_cast<const uint4 *>(pp + (l - 1));  // hide the LDS latency of the next step
         if (!(e.y & 0x80000000u)) {
-          // escape: payload nibbles MSB first, then the count nibble (we walk the entry list backwards)
+          // escape: the entry list read backwards is payload nibbles MSB..LSB, then the count nibble, i.e. the
+          // (nb+1)-nibble integer V = raw << 4 | nb pushed MSB first.  The reference renormalises before a nibble
+          // iff x >= 2^59 (rans_interface.cpp:69-87); with L = bitlen(x) exactly J = (59 - L) / 4 + 1 nibbles fit
+          // before that happens, so nibbles are pushed in groups (at most 3 rounds) instead of one by one.
           const uint32_t raw = rr[l];
           const int nb = raw ? ((35 - __clz(raw)) >> 2) : 0;
-          for (int t = nb - 1; t >= 0; --t) {
-            if (static_cast<uint32_t>(x >> 32) >= (1u << 27)) {  // x >= 2^59
+          const uint64_t V = (static_cast<uint64_t>(raw) << 4) | static_cast<uint32_t>(nb);
+          int rem = nb + 1;
+          while (rem > 0) {
+            const int L = 64 - __clzll(x);
+            if (L > 59) {
               em.push(static_cast<uint32_t>(x));
               x >>= 32;
+              continue;
             }
-            x = (x << 4) | ((raw >> (4 * t)) & 15u);
+            const int J = ((59 - L) >> 2) + 1;
+            const int c = J < rem ? J : rem;
+            const uint64_t part = (V >> (4 * (rem - c))) & ((1ull << (4 * c)) - 1ull);
+            x = (x << (4 * c)) | part;
+            rem -= c;
           }
-          if (static_cast<uint32_t>(x >> 32) >= (1u << 27)) {
-            em.push(static_cast<uint32_t>(x));
-            x >>= 32;
-          }
-          x = (x << 4) | static_cast<uint32_t>(nb);
         }
-        if (static_cast<uint32_t>(x >> 32) >= e.w) {
-          em.push(static_cast<uint32_t>(x));
-          x >>= 32;
-        }
+        // Rans64EncPut (rans64.h:77-93): renormalise iff x >= freq << 47, then x = x + bias + (x / freq) * (2^16 - freq)
+        const uint32_t xh = static_cast<uint32_t>(x >> 32);
+        const bool rn = xh >= e.w;
+        em.push_if(rn, static_cast<uint32_t>(x));
+        x = rn ? static_cast<uint64_t>(xh) : x;
         const uint64_t m = (static_cast<uint64_t>(e.y | 0x80000000u) << 32) | e.x;
         const uint32_t shift = e.z >> 20;
         const uint32_t bias = e.z & 0xFFFFFu;
@@ -287,31 +301,33 @@ rans_encode_kernel(const unsigned char *__restrict__ blob, uint32_t enc_bytes, c
 // ---- decoder -------------------------------------------------------------------------------------------
 struct WordFeed {
   const uint32_t *w;
-  int64_t nw;
-  int64_t pos;    // next word to consume
-  int64_t cbase;  // multiple of 32: wcur holds [cbase, cbase+32)
+  uint32_t nw;     // words in this string (< 2^31)
+  uint32_t pos;    // next word to consume
+  uint32_t cbase;  // multiple of 32: wcur holds [cbase, cbase+32), wnext the following 32
   uint32_t wcur, wnext, next;
-  int lane;
-  __device__ __forceinline__ uint32_t load(int64_t base) const {
-    const int64_t i = base + lane;
-    return (i >= 0 && i < nw) ? __ldg(w + i) : 0u;
+  uint32_t lane;
+  __device__ __forceinline__ uint32_t load(uint32_t base) const {
+    const uint32_t i = base + lane;
+    return (i < nw) ? __ldg(w + i) : 0u;
   }
-  __device__ __forceinline__ void init(int64_t p) {
+  __device__ __forceinline__ void init(uint32_t p) {
     pos = p;
-    cbase = p & ~static_cast<int64_t>(31);
+    cbase = p & ~31u;
     wcur = load(cbase);
-    wnext = load(cbase + 32);
-    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31));
+    wnext = load(cbase + 32u);
+    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31u));
   }
+  // consume one word; the following word is fetched from the lane buffers right away so that it is already
+  // in a register when the next renormalisation needs it (off the critical path)
   __device__ __forceinline__ uint32_t take() {
     const uint32_t r = next;
     pos += 1;
-    if ((pos & 31) == 0) {
+    if ((pos & 31u) == 0) {
       wcur = wnext;
-      cbase += 32;
-      wnext = load(cbase + 32);
+      cbase += 32u;
+      wnext = load(cbase + 32u);
     }
-    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31));
+    next = __shfl_sync(0xffffffffu, wcur, static_cast<int>(pos & 31u));
     return r;
   }
 };
@@ -356,12 +372,12 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
 
     WordFeed wf;
     wf.w = words + word_begin[b];
-    wf.nw = word_count ? static_cast<int64_t>(word_count[b]) : (word_begin[b + 1] - word_begin[b]);
-    wf.lane = lane;
+    wf.nw = static_cast<uint32_t>(word_count ? static_cast<int64_t>(word_count[b]) : (word_begin[b + 1] - word_begin[b]));
+    wf.lane = static_cast<uint32_t>(lane);
     uint64_t x;
     if (resume && state) {
       x = state[2 * b];
-      wf.init(static_cast<int64_t>(state[2 * b + 1]));
+      wf.init(static_cast<uint32_t>(state[2 * b + 1]));
     } else {
       wf.init(0);
       const uint32_t lo = wf.take();
@@ -398,9 +414,11 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
       const int64_t rem = n - (j << 5);
       const int nvalid = rem < 32 ? static_cast<int>(rem) : 32;
       int32_t myout = 0;
+      uint4 d_next = *reinterpret_cast<const uint4 *>(pp);
 #pragma unroll 2
       for (int l = 0; l < nvalid; ++l) {
-        const uint4 d = *reinterpret_cast<const uint4 *>(pp + l);
+        const uint4 d = d_next;
+        if (l + 1 < nvalid) d_next = *reinterpret_cast<const uint4 *>(pp + (l + 1));  // prefetch next parameters
         const int32_t maxv = static_cast<int32_t>(d.y);
         const uint32_t cf = static_cast<uint32_t>(x) & 0xFFFFu;
         const uint2 e = lut[d.w + (cf >> lut_shift)];
@@ -408,27 +426,40 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
         uint32_t freq = e.x >> 16;
         int32_t s = static_cast<int32_t>(e.y);
         if (freq == 0) {
-          // bucket spans several symbols: warp-cooperative forward search from s
-          const int32_t last = maxv + 1;  // position of the terminal entry (acts as +infinity)
+          // bucket spans several symbols: warp-cooperative forward search from s.  Lane i tests symbol s + i
+          // (cdf[s+i] <= cf < cdf[s+i+1]); exactly one lane can hit, and a max-reduction broadcasts its
+          // (freq, start) pair without a second round of dependent shared-memory loads.
           for (;;) {
             const int32_t cand = s + lane;
-            const bool hit = (cand + 1 >= last) || (static_cast<uint32_t>(cdf16[d.x + cand + 1]) > cf);
-            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
-            if (ball) {
-              s += __ffs(ball) - 1;
+            uint32_t packed = 0;
+            if (cand <= maxv) {
+              const uint32_t c_lo = cdf16[d.x + cand];
+              const uint32_t c_hi = (cand == maxv) ? 0x10000u : static_cast<uint32_t>(cdf16[d.x + cand + 1]);
+              if (c_lo <= cf && cf < c_hi) packed = ((c_hi - c_lo) << 16) | c_lo;
+            }
+            const uint32_t win = __reduce_max_sync(0xffffffffu, packed);
+            if (win) {
+              s += __ffs(__ballot_sync(0xffffffffu, packed != 0)) - 1;
+              start = win & 0xFFFFu;
+              freq = win >> 16;
               break;
             }
             s += 32;
+            if (s > maxv) {  // malformed table: stay in bounds, keep the chain defined
+              s = maxv < 0 ? 0 : maxv;
+              start = cdf16[d.x + s];
+              freq = 1;
+              break;
+            }
           }
-          if (s > maxv) s = maxv < 0 ? 0 : maxv;
-          start = cdf16[d.x + s];
-          freq = (static_cast<uint32_t>(cdf16[d.x + s + 1]) - start) & 0xFFFFu;
         }
         x = static_cast<uint64_t>(freq) * (x >> 16) + (cf - start);
         if (x < (1ull << 31)) x = (x << 32) | wf.take();
         int32_t v = s;
         if (s == maxv) {
-          // bypass / escape decoding (rans_interface.cpp:256-278)
+          // bypass / escape decoding (rans_interface.cpp:256-278).  Count nibble(s) one at a time, then the
+          // payload nibbles in groups: with L = bitlen(x), the reference refills after pop number
+          // ceil((L - 31) / 4) (that pop leaves x < 2^31), so that many nibbles can be taken at once.
           uint32_t t = static_cast<uint32_t>(x) & 15u;
           x >>= 4;
           if (x < (1ull << 31)) x = (x << 32) | wf.take();
@@ -439,13 +470,22 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
             if (x < (1ull << 31)) x = (x << 32) | wf.take();
             nb += static_cast<int32_t>(t);
           }
-          uint32_t raw = 0;
-          for (int32_t q = 0; q < nb; ++q) {
-            const uint32_t nib = static_cast<uint32_t>(x) & 15u;
-            x >>= 4;
-            if (x < (1ull << 31)) x = (x << 32) | wf.take();
-            if (q < 8) raw |= nib << (4 * q);
+          uint64_t acc = 0;
+          int done = 0;
+          int rem = nb;
+          while (rem > 0) {
+            const int L = 64 - __clzll(x);
+            int js = (L - 31 + 3) >> 2;
+            if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
+            const int c = rem < js ? rem : js;
+            const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
+            x >>= 4 * c;
+            if (done < 8) acc |= bits << (4 * done);
+            done += c;
+            rem -= c;
+            if (c == js) x = (x << 32) | wf.take();
           }
+          const uint32_t raw = static_cast<uint32_t>(acc);
           const int32_t sraw = static_cast<int32_t>(raw);
           v = sraw >> 1;
           v = (sraw & 1) ? (-v - 1) : (v + maxv);
@@ -519,9 +559,14 @@ int64_t cai_rans_slot_words(int64_t n_symbols) {
 }
 
 static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
-  int w = (B + dp.sm_count - 1) / dp.sm_count;
-  if (w < 1) w = 1;
+  // A string is a serial chain: its warp issues ~0.2 instructions per cycle, so several strings share an SM
+  // sub-partition without slowing each other much.  Few, fat CTAs (>= 8 warps) keep the coder on a handful of
+  // SMs -- each CTA pins a copy of the table in shared memory -- and leave the rest of the chip to the
+  // transform kernels running concurrently on other streams.
+  int w = (B + dp.sm_count / 4 - 1) / (dp.sm_count / 4 > 0 ? dp.sm_count / 4 : 1);
+  if (w < 8) w = 8;
   if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+  if (w > B) w = B < 1 ? 1 : B;
   int g = (B + w - 1) / w;
   if (g > dp.sm_count) g = dp.sm_count;  // persistent: each warp strides over strings
   if (g < 1) g = 1;

@@ -112,6 +112,7 @@ class EntropyModel(nn.Module):
         attributes = self.__dict__.copy()
         attributes["entropy_coder"] = self.entropy_coder.name
         attributes["_table_cache"] = None
+        attributes.pop("_scalar_cache", None)
         return attributes
 
     def __setstate__(self, state):
@@ -132,8 +133,22 @@ class EntropyModel(nn.Module):
 
     forward: Callable[..., Any] = _forward
 
+    @staticmethod
+    def _cached_scalar(owner, buf):
+        """Host copy of a 1-element buffer, refreshed only when the buffer changes (avoids a device->host sync
+        per call: the codec path must stay asynchronous so that chunks can overlap)."""
+        key = (buf.data_ptr(), buf._version)
+        cache = owner.__dict__.setdefault("_scalar_cache", {})
+        hit = cache.get(id(buf))
+        if hit is None or hit[0] != key:
+            hit = (key, float(buf.item()))
+            cache[id(buf)] = hit
+        return hit[1]
+
     def _lik_bound(self) -> float:
-        return float(self.likelihood_lower_bound.bound.item()) if self.use_likelihood_bound else 0.0
+        if not self.use_likelihood_bound:
+            return 0.0
+        return self._cached_scalar(self, self.likelihood_lower_bound.bound)
 
     # ---- quantisation ---------------------------------------------------------------------------------
     def quantize(self, inputs: Tensor, mode: str, means: Optional[Tensor] = None) -> Tensor:
@@ -616,7 +631,7 @@ class GaussianConditional(EntropyModel):
         self._cdf_length = pmf_length + 2
 
     def _bound_scale(self) -> float:
-        return float(self.lower_bound_scale.bound.item())
+        return self._cached_scalar(self, self.lower_bound_scale.bound)
 
     def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None) -> Tensor:
         _, lik = _GaussianLikelihood.apply(inputs, scales, means, None, 2, self._bound_scale(), 0.0)

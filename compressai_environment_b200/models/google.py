@@ -16,6 +16,7 @@ import warnings
 import torch
 import torch.nn as nn
 
+from .. import _lib, coder, kernels
 from ..entropy_models import EntropyBottleneck, GaussianConditional
 from ..layers import GDN
 from ..transforms import TransformStack
@@ -100,15 +101,17 @@ class FactorizedPrior(CompressionModel):
         net.load_state_dict(state_dict)
         return net
 
+    @torch.no_grad()
     def compress(self, x):
         y = self.g_a(_nhwc(x))
         y_strings = self.entropy_bottleneck.compress(y)
         return {"strings": [y_strings], "shape": y.size()[-2:]}
 
+    @torch.no_grad()
     def decompress(self, strings, shape):
         assert isinstance(strings, list) and len(strings) == 1
         y_hat = self.entropy_bottleneck.decompress(strings[0], shape, memory_format=_CL)
-        x_hat = self.g_s(y_hat).clamp_(0, 1)
+        x_hat = self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True)
         return {"x_hat": x_hat}
 
 
@@ -141,6 +144,8 @@ class ScaleHyperprior(CompressionModel):
     @property
     def downsampling_factor(self) -> int:
         return 2 ** (4 + 2)
+
+    _abs_hyper_input = True
 
     def _hyper_in(self, y):
         return torch.abs(y)
@@ -178,39 +183,160 @@ class ScaleHyperprior(CompressionModel):
         updated |= super().update(force=force)
         return updated
 
-    def compress(self, x):
-        y = self.g_a(_nhwc(x))
-        z = self.h_a(self._hyper_in(y))
-        z_enc, z_hat = self.entropy_bottleneck.compress_symbols(z)
-        scales_hat, means_hat = self._params(z_hat)
-        y_enc, _ = self.gaussian_conditional.compress_from_scales(y, scales_hat, means_hat)
-        return {"strings": [y_enc.to_bytes(), z_enc.to_bytes()], "shape": z.size()[-2:]}
+    # Transforms run in micro-batches (activation memory), the coder runs ONCE per tensor for the whole batch: a
+    # rANS string is a serial chain, so the launch latency is that of one string however many strings it codes.
+    micro_batch = 32
 
+    def _analysis_chunk(self, x):
+        """g_a + h_a + hyper-latent quantisation + h_s for one micro-batch (inference)."""
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        if self._abs_hyper_input:
+            y, y_abs = self.g_a(x, want_abs=True)
+            z = self.h_a(y_abs)
+        else:
+            y = self.g_a(x)
+            z = self.h_a(y)
+        z_sym, z_idx = kernels.eb_quantize_index(z, eb._get_medians())
+        z_hat = kernels.dequantize(z_sym, None, eb._get_medians(), tuple(z.shape), _CL)
+        scales_hat, means_hat = self._params(z_hat)
+        y_sym, y_idx = kernels.gc_quantize_index(y, scales_hat, means_hat, gc.scale_table, gc._bound_scale())
+        return y_sym, y_idx, z_sym, z_idx, z.size()[-2:]
+
+    # ---- stream plan ------------------------------------------------------------------------------------------
+    # "ana": analysis transforms of all chunks, in chunk order.  "syn": synthesis transforms, in chunk order.
+    # "coder[k]": the serial-chain coder kernels of chunk k (high priority: they need one SM each, for long).
+    # A chunk's coder latency (tens of ms, a few SMs) then overlaps the tensor-core work of the other chunks, and
+    # because nothing here synchronises the host, the analysis of the NEXT call overlaps this call's decode wait.
+    max_streams = 8
+
+    def _streams(self, device, n):
+        pool = self.__dict__.setdefault("_stream_pool", {})
+        st = pool.get(str(device))
+        if st is None:
+            st = {"ana": torch.cuda.Stream(device=device), "syn": torch.cuda.Stream(device=device), "coder": []}
+            pool[str(device)] = st
+        while len(st["coder"]) < n:
+            st["coder"].append(torch.cuda.Stream(device=device, priority=-1))
+        return st
+
+    @staticmethod
+    def _handoff(stream, *tensors):
+        """Tensors produced on the current stream are about to be consumed on ``stream``."""
+        ev = torch.cuda.current_stream().record_event()
+        stream.wait_event(ev)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(stream)
+
+    def _check_tables(self):
+        for m in (self.entropy_bottleneck, self.gaussian_conditional):
+            m._check_cdf_size()
+            m._check_cdf_length()
+            m._check_offsets_size()
+
+    @torch.no_grad()
+    def compress_to_device(self, x):
+        """compress() with the strings left in HBM: per micro-batch ``coder.EncodedBatch`` lists."""
+        self._check_tables()
+        _lib.require_cuda(x, "inputs")
+        eb_t, gc_t = self.entropy_bottleneck._table(), self.gaussian_conditional._table()
+        starts = list(range(0, x.size(0), self.micro_batch))
+        S = self._streams(x.device, min(len(starts), self.max_streams))
+        ana = S["ana"]
+        ana.wait_event(torch.cuda.current_stream(x.device).record_event())
+        x.record_stream(ana)
+        y_encs, z_encs, shape = [], [], None
+        for k, i in enumerate(starts):
+            ck = S["coder"][k % len(S["coder"])]
+            with torch.cuda.stream(ana):
+                y_sym, y_idx, z_sym, z_idx, shape = self._analysis_chunk(x[i:i + self.micro_batch])
+                self._handoff(ck, y_sym, y_idx, z_sym, z_idx)
+            with torch.cuda.stream(ck):
+                z_encs.append(coder.encode(eb_t, z_sym, z_idx))
+                y_encs.append(coder.encode(gc_t, y_sym, y_idx))
+                z_encs[-1].stream = y_encs[-1].stream = ck
+        return {"strings": [y_encs, z_encs], "shape": shape}
+
+    def compress(self, x):
+        out = self.compress_to_device(x)
+        y_encs, z_encs = out["strings"]
+        ys, zs = [], []
+        for ye, ze in zip(y_encs, z_encs):
+            with torch.cuda.stream(ye.stream):
+                ys += ye.to_bytes()
+                zs += ze.to_bytes()
+        return {"strings": [ys, zs], "shape": out["shape"]}
+
+    @torch.no_grad()
+    def _decompress_chunks(self, chunks, shape, device):
+        """chunks: list of (coder_stream, y_words, z_words, n) with *_words = (strings | None, device_words | None)."""
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        eb_t, gc_t = eb._table(), gc._table()
+        S = self._streams(device, 1)
+        syn = S["syn"]
+        main = torch.cuda.current_stream(device)
+        syn.wait_event(main.record_event())
+        C = eb._quantized_cdf.size(0)
+        h, w = int(shape[0]), int(shape[1])
+        # pass 1 (all chunks): z decode -> h_s -> indexes -> launch the y decode.  pass 2: dequantize + g_s.
+        # "syn" is in order, so issuing every h_s before any g_s keeps one chunk's y-decode latency from
+        # blocking the next chunk's hyper-synthesis.
+        ready = main.record_event()
+        pending = []
+        for ck, y_words, z_words, n in chunks:
+            with torch.cuda.stream(ck):
+                ck.wait_event(ready)
+                z_idx = kernels.channel_indexes(n, C, h * w, device)
+                z_sym = coder.decode(eb_t, z_words[0], z_idx, device_words=z_words[1])
+                self._handoff(syn, z_sym)
+            with torch.cuda.stream(syn):
+                z_hat = kernels.dequantize(z_sym, None, eb._get_medians(), (n, C, h, w), _CL)
+                scales_hat, means_hat = self._params(z_hat)
+                _, y_idx = kernels.gc_quantize_index(None, scales_hat, None, gc.scale_table, gc._bound_scale())
+                self._handoff(ck, y_idx)
+            with torch.cuda.stream(ck):
+                y_sym = coder.decode(gc_t, y_words[0], y_idx, device_words=y_words[1])
+                done = ck.record_event()  # "syn" must NOT wait here: that would serialise the chunks' decodes
+                y_sym.record_stream(syn)
+            pending.append((y_sym, means_hat, tuple(scales_hat.shape), done))
+        outs = []
+        with torch.cuda.stream(syn):
+            for y_sym, means_hat, shp, done in pending:
+                syn.wait_event(done)
+                y_hat = kernels.dequantize(y_sym, means_hat, None, shp, _CL)
+                outs.append(self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True))
+        with torch.cuda.stream(syn):
+            x_hat = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        main.wait_event(syn.record_event())
+        x_hat.record_stream(main)
+        return {"x_hat": x_hat}
+
+    @torch.no_grad()
     def decompress(self, strings, shape):
         assert isinstance(strings, list) and len(strings) == 2
-        z_hat = self.entropy_bottleneck.decompress(strings[1], shape, memory_format=_CL)
-        scales_hat, means_hat = self._params(z_hat)
-        y_hat = self.gaussian_conditional.decompress_from_scales(strings[0], scales_hat, means_hat)
-        x_hat = self.g_s(y_hat).clamp_(0, 1)
-        return {"x_hat": x_hat}
+        self._check_tables()
+        if len(strings[0]) != len(strings[1]):
+            raise ValueError("Invalid strings or indexes parameters")
+        dev = self.gaussian_conditional._quantized_cdf.device
+        _lib.require_cuda(self.gaussian_conditional._quantized_cdf, "model buffers")
+        n = len(strings[0])
+        starts = list(range(0, n, self.micro_batch))
+        S = self._streams(dev, min(max(len(starts), 1), self.max_streams))
+        chunks = []
+        for k, i in enumerate(starts):
+            ys, zs = list(strings[0][i:i + self.micro_batch]), list(strings[1][i:i + self.micro_batch])
+            chunks.append((S["coder"][k % len(S["coder"])], (ys, None), (zs, None), len(ys)))
+        return self._decompress_chunks(chunks, shape, dev)
 
-    # ---- device-resident variants (same kernels, strings never leave HBM): used for kernel-only timing ----
-    def compress_to_device(self, x):
-        y = self.g_a(_nhwc(x))
-        z = self.h_a(self._hyper_in(y))
-        z_enc, z_hat = self.entropy_bottleneck.compress_symbols(z)
-        scales_hat, means_hat = self._params(z_hat)
-        y_enc, _ = self.gaussian_conditional.compress_from_scales(y, scales_hat, means_hat)
-        return {"strings": [y_enc, z_enc], "shape": z.size()[-2:]}
-
+    @torch.no_grad()
     def decompress_from_device(self, enc, shape):
-        y_enc, z_enc = enc
-        z_hat = self.entropy_bottleneck.decompress(None, shape, memory_format=_CL, device_words=z_enc.device_words())
-        scales_hat, means_hat = self._params(z_hat)
-        y_hat = self.gaussian_conditional.decompress_from_scales(None, scales_hat, means_hat,
-                                                                 device_words=y_enc.device_words())
-        x_hat = self.g_s(y_hat).clamp_(0, 1)
-        return {"x_hat": x_hat}
+        y_encs, z_encs = enc
+        dev = y_encs[0].slots.device
+        chunks = []
+        for ye, ze in zip(y_encs, z_encs):
+            with torch.cuda.stream(ye.stream):  # the word offsets are derived from n_words on the coder stream
+                chunks.append((ye.stream, (None, ye.device_words()), (None, ze.device_words()), int(ye.n_words.numel())))
+        return self._decompress_chunks(chunks, shape, dev)
 
 
 class MeanScaleHyperprior(ScaleHyperprior):
@@ -222,6 +348,8 @@ class MeanScaleHyperprior(ScaleHyperprior):
                                  nn.LeakyReLU(inplace=True), conv(N, N))
         self.h_s = TransformStack(deconv(N, M), nn.LeakyReLU(inplace=True), deconv(M, M * 3 // 2),
                                  nn.LeakyReLU(inplace=True), conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+
+    _abs_hyper_input = False
 
     def _hyper_in(self, y):
         return y
