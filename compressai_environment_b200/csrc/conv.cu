@@ -56,6 +56,10 @@ struct ConvKernelParams {
   int epilogue;                      // 0 linear, 1 relu, 2 leaky relu (0.01), 3 gdn (aux * rsqrt), 4 igdn (aux * sqrt)
   float clamp_lo, clamp_hi;          // applied when clamp_lo < clamp_hi
   int stages;
+  // fused GDN / IGDN (second in-kernel GEMM): norm = gamma . out^2 + beta ; out = out * rsqrt(norm) (or * sqrt)
+  const unsigned char *gdn_w;        // packed gamma: [kc][hi | lo][BN x 64 bf16], NULL = no fusion
+  const float *gdn_beta;             // [Cout]
+  int gdn_mode;                      // 1 GDN, 2 IGDN
   int8_t dy[kMaxTaps], dx[kMaxTaps];
 };
 
@@ -127,6 +131,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -150,6 +163,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   __shared__ __align__(8) uint64_t full_bar[4];
   __shared__ __align__(8) uint64_t empty_bar[4];
   __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc2_bar;
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x;
@@ -165,8 +179,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const int n_tile = blockIdx.y;
   const int n0 = n_tile * BN;
 
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(BN)) tmem_cols <<= 1;
+  const bool fuse_gdn = p.gdn_w != nullptr;
+  const int gdn_ksteps = fuse_gdn ? (BN + kBK - 1) / kBK : 0;
+  uint32_t acc_cols = 32;
+  while (acc_cols < static_cast<uint32_t>(BN)) acc_cols <<= 1;
+  const uint32_t tmem_cols = fuse_gdn ? 2 * acc_cols : acc_cols;  // second accumulator at column acc_cols
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
+    mbar_init(&acc2_bar, 1);
     mbar_fence_init();
   }
   if (warp == 4) {
@@ -249,15 +267,58 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     // ===================== epilogue: thread = TMEM lane = pixel row =====================
     mbar_wait_bounded(&acc_bar, 0);
     tc_fence_after();
+    const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
+    if (fuse_gdn) {
+      // ---- fused GDN, part 1: turn the accumulator into the A operand of the second GEMM.
+      // x = acc + bias; x^2 is split into bf16 planes and written, 64 channels (one k-step) at a time, into the
+      // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
+      for (int g = 0; g < gdn_ksteps; ++g) {
+        const int ks = ksteps + g;
+        const int s = ks % stages;
+        if (ks >= stages) mbar_wait_bounded(&empty_bar[s], ((ks / stages) - 1) & 1);
+        unsigned char *sa = smem + static_cast<size_t>(s) * stage_bytes;
+        if (tid == 0) {
+          mbar_expect_tx(&full_bar[s], 2 * b_plane);
+          tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
+        }
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          const int col = g * kBK + c * 8;
+          uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
+          if (col < BN) {  // warp-uniform
+            uint32_t raw[8];
+            tmem_ld8(tmem_base + lane_base + static_cast<uint32_t>(col), raw);
+            float sq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a = __uint_as_float(raw[i]);
+              if (p.bias) a += __ldg(p.bias + n0 + col + i);
+              sq[i] = a * a;
+            }
+            const Pack8 pk = split8(sq);
+            vh = pk.hi;
+            vl = pk.lo;
+          }
+          const uint32_t so = static_cast<uint32_t>(c) * (kBM * 16u) + row_off;
+          *reinterpret_cast<uint4 *>(sa + so) = vh;
+          *reinterpret_cast<uint4 *>(sa + a_plane + so) = vl;
+        }
+        fence_async_proxy();
+        mbar_arrive(&full_bar[s]);
+      }
+      mbar_wait_bounded(&acc2_bar, 0);
+      tc_fence_after();
+    }
     int64_t opix = 0;
     if (row_ok) {
       const int oy = pi * p.os + p.o0y, ox = pj * p.os + p.o0x;
       opix = (static_cast<int64_t>(n_img) * p.Ho + oy) * p.Wo + ox;
     }
-    const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t raw[16];
       tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
+      uint32_t raw2[16];
+      if (fuse_gdn) tmem_ld16(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
       if (!row_ok) continue;
       const int cg = n0 + c0;  // global output channel of raw[0]
       if (cg >= p.Cout) continue;
@@ -267,6 +328,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         float a = __uint_as_float(raw[i]);
         if (p.bias && cg + i < p.Cout) a += __ldg(p.bias + cg + i);
         v[i] = a;
+      }
+      if (fuse_gdn) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float nrm = __uint_as_float(raw2[i]) + __ldg(p.gdn_beta + cg + i);
+          v[i] = (p.gdn_mode == 1) ? v[i] * rsqrtf(nrm) : v[i] * sqrtf(nrm);
+        }
       }
       const int64_t obase = opix * p.Cout + cg;
       if (p.epilogue == 1) {
@@ -338,11 +406,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                            (static_cast<uint32_t>(kBM >> 4) << 24);
     const uint32_t lbo_a = kBM * 16u, lbo_b = static_cast<uint32_t>(BN) * 16u;
-    for (int ks = 0; ks < ksteps; ++ks) {
+    for (int ks = 0; ks < ksteps + gdn_ksteps; ++ks) {
       const int s = ks % stages;
       mbar_wait_bounded(&full_bar[s], (ks / stages) & 1);
       tc_fence_after();
       if (lane == 0) {
+        const bool second = ks >= ksteps;  // GDN GEMM: A = x^2 planes written by the epilogue warps, B = gamma
+        const uint32_t d_tmem = second ? tmem_base + acc_cols : tmem_base;
+        const int first_ks = second ? ksteps : 0;
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
         const uint32_t a_hi = sa, a_lo = sa + a_plane, b_hi = sa + 2 * a_plane, b_lo = b_hi + b_plane;
 #pragma unroll
@@ -351,12 +422,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, 128);
           const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
           const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, 128);
-          umma_bf16(tmem_base, dah, dbh, idesc, (ks | kk) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+          umma_bf16(d_tmem, dah, dbh, idesc, (ks > first_ks || kk > 0) ? 1u : 0u);
+          umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+          umma_bf16(d_tmem, dal, dbh, idesc, 1u);
         }
-        umma_commit(&empty_bar[s]);                    // frees the smem stage when the MMAs have read it
-        if (ks == ksteps - 1) umma_commit(&acc_bar);   // accumulator complete
+        umma_commit(&empty_bar[s]);                         // frees the smem stage when the MMAs have read it
+        if (ks == ksteps - 1) umma_commit(&acc_bar);        // main accumulator complete
+        if (second && ks == ksteps + gdn_ksteps - 1) umma_commit(&acc2_bar);  // norm accumulator complete
       }
       __syncwarp();
     }
@@ -525,6 +597,14 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   if (stages > ksteps) stages = ksteps < 2 ? 2 : ksteps;
   CAI_CHECK_ARG(stages >= 2, "cai_conv_gemm: tile does not fit shared memory");
   p.stages = stages;
+  p.gdn_w = static_cast<const unsigned char *>(d->gdn_w);
+  p.gdn_beta = d->gdn_beta;
+  p.gdn_mode = d->gdn_mode;
+  if (p.gdn_w) {
+    CAI_CHECK_ARG(d->BN == d->Cout && d->BN <= 256, "cai_conv_gemm: fused GDN needs all channels in one tile (Cout <= 256)");
+    CAI_CHECK_ARG(d->gdn_beta && (d->gdn_mode == 1 || d->gdn_mode == 2), "cai_conv_gemm: fused GDN needs beta and mode 1|2");
+    CAI_CHECK_ARG(d->epilogue == 0, "cai_conv_gemm: fused GDN excludes another epilogue");
+  }
   const size_t smem = stages * stage_bytes;
   const int64_t M_total = static_cast<int64_t>(d->N) * d->Hp * d->Wp;
   const int64_t mt = (M_total + kBM - 1) / kBM;

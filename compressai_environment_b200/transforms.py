@@ -274,8 +274,10 @@ def _prep_gdn(m) -> _Layer:
 
 # ---- launches -------------------------------------------------------------------------------------------------
 def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o0x, is_, epilogue=0, aux: Planes = None,
-            out_f32=None, out: Planes = None, sq: Planes = None, ab: Planes = None, clamp=None):
+            out_f32=None, out: Planes = None, sq: Planes = None, ab: Planes = None, clamp=None, gdn=None):
     d = ConvDesc()
+    if gdn is not None:  # fused GDN / IGDN: (packed gamma, beta, mode)
+        d.gdn_w, d.gdn_beta, d.gdn_mode = gdn[0].data_ptr(), gdn[1].data_ptr(), gdn[2]
     d.a_hi, d.a_lo, d.w_packed = a.hi.data_ptr(), a.lo.data_ptr(), packed.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     if aux is not None:
@@ -309,7 +311,7 @@ def _outputs(N, Ho, Wo, C, device, want):
     return out_f32, out, sq, ab
 
 
-def _run_conv(m, x, act, want, clamp=None):
+def _run_conv(m, x, act, want, clamp=None, gdn=None):
     """x: Planes (or fp32 tensor for the im2col first layer). Returns (f32 NHWC tensor | None, planes, sq, abs)."""
     lay = _prep_conv(m)
     dev = m.weight.device
@@ -332,7 +334,7 @@ def _run_conv(m, x, act, want, clamp=None):
                                          current_stream()), "cai_im2col_split")
         o = _outputs(N, Ho, Wo, lay.cout, dev, want)
         _launch(a, lay.packed, lay.bias, [(0, 0)], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, 1, _ACT[act], None, *o,
-                clamp=clamp)
+                clamp=clamp, gdn=gdn)
         return o
     if not isinstance(x, Planes):
         x = to_planes(x, lay.cin)
@@ -340,11 +342,11 @@ def _run_conv(m, x, act, want, clamp=None):
     Ho, Wo = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
     o = _outputs(x.N, Ho, Wo, lay.cout, dev, want)
     _launch(x, lay.packed, lay.bias, lay.phases[0], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, s, _ACT[act], None, *o,
-            clamp=clamp)
+            clamp=clamp, gdn=gdn)
     return o
 
 
-def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False):
+def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None):
     lay = _prep_deconv(m)
     dev = m.weight.device
     if not isinstance(x, Planes):
@@ -382,7 +384,7 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False):
             if not taps:
                 raise _lib.CaiError("transposed convolution phase without taps is not supported (kernel < stride)")
             _launch(x, blob, lay.bias, taps, lay.bn, lay.cout, Ho, Wo, Hp, Wp, s, py, px, 1, _ACT[act], None, *o,
-                    clamp=clamp)
+                    clamp=clamp, gdn=gdn)
     return o
 
 
@@ -417,6 +419,27 @@ def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw
                 act, consumed = "leaky", 2
             after = mods[i + consumed] if i + consumed < n else None
             last = after is None
+            fused = None
+            if isinstance(after, GDN) and act is None:
+                glay = _prep_gdn(after)
+                width = _prep_conv(m).cout if isinstance(m, Conv2d) else _prep_deconv(m).cout
+                kind_ok = not (isinstance(m, ConvTranspose2d) and m.out_channels <= 4)
+                if kind_ok and glay.cout == width and width <= 256 and glay.bn == width:
+                    fused = (glay.packed, glay.bias, 2 if glay.kind == "igdn" else 1)
+            if fused is not None:
+                # conv + GDN in ONE launch (second in-kernel GEMM): the pre-GDN activation never leaves the SM
+                glast = i + consumed + 1 >= n
+                want = (("f32", "abs") if want_abs else ("f32",)) if glast else ("planes",)
+                if isinstance(m, Conv2d):
+                    o = _run_conv(m, cur, None, want, clamp if glast else None, gdn=fused)
+                else:
+                    o = _run_deconv(m, cur, None, want, clamp if glast else None, gdn=fused)
+                i += consumed + 1
+                if glast:
+                    result = (o[0], o[3])
+                else:
+                    cur = o[1]
+                continue
             if isinstance(after, GDN):
                 want = ("planes", "sq")
             elif last:

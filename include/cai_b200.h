@@ -247,6 +247,13 @@ typedef struct cai_conv_desc {
   int32_t epilogue;
   float clamp_lo, clamp_hi;  /* clamp applied when clamp_lo < clamp_hi */
   int8_t dy[32], dx[32];
+  /* Fused GDN / IGDN (compressai/layers/gdn.py:77-92) as a second in-kernel GEMM: with v = D + bias,
+   * out = v * rsqrt(gamma . v^2 + beta) (gdn_mode 1) or v * sqrt(...) (gdn_mode 2).  gdn_w = gamma packed like
+   * w_packed with one tap ([kchunk][hi | lo][Cout x 64 bf16]); needs BN == Cout <= 256 and epilogue == 0.
+   * NULL = no fusion. */
+  const void *gdn_w;
+  const float *gdn_beta;
+  int32_t gdn_mode;
 } cai_conv_desc;
 
 int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream);
