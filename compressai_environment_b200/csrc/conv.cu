@@ -31,7 +31,7 @@
 namespace cai {
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
-constexpr int kBK = 64;           // k elements per stage (4 x UMMA_K=16)
+constexpr int kBK = 32;           // k elements per stage (2 x UMMA_K=16): small stages -> 2 CTAs per SM
 constexpr int kProducerThreads = 128;
 constexpr int kConvThreads = 160;
 constexpr int kMaxTaps = 32;
@@ -39,7 +39,7 @@ constexpr uint32_t kSpinLimit = 1u << 28;
 
 struct ConvKernelParams {
   const __nv_bfloat16 *a_hi, *a_lo;  // [N, H, W, Cin] bf16 planes
-  const unsigned char *w_packed;     // [n_tiles][ksteps][hi | lo] each BN x 64 bf16, canonical layout
+  const unsigned char *w_packed;     // [n_tiles][ksteps][hi | lo] each BN x kBK bf16, canonical layout
   const float *bias;                 // [Cout] or NULL
   const __nv_bfloat16 *aux_hi, *aux_lo;  // [M_out_pixels, Cout] planes for the GDN finalize, or NULL
   float *out_f32;                    // [N, Ho, Wo, Cout] or NULL
@@ -51,13 +51,13 @@ struct ConvKernelParams {
   int os, o0y, o0x;                  // output pixel = (i * os + o0y, j * os + o0x)
   int is;                            // input pixel  = (i * is + dy[t], j * is + dx[t])
   int ntaps;
-  int kchunks;                       // ceil(Cin / 64)
+  int kchunks;                       // ceil(Cin / kBK)
   int BN;                            // output channels per tile (multiple of 16, <= 256)
   int epilogue;                      // 0 linear, 1 relu, 2 leaky relu (0.01), 3 gdn (aux * rsqrt), 4 igdn (aux * sqrt)
   float clamp_lo, clamp_hi;          // applied when clamp_lo < clamp_hi
   int stages;
   // fused GDN / IGDN (second in-kernel GEMM): norm = gamma . out^2 + beta ; out = out * rsqrt(norm) (or * sqrt)
-  const unsigned char *gdn_w;        // packed gamma: [kc][hi | lo][BN x 64 bf16], NULL = no fusion
+  const unsigned char *gdn_w;        // packed gamma: [kc][hi | lo][BN x kBK bf16], NULL = no fusion
   const float *gdn_beta;             // [Cout]
   int gdn_mode;                      // 1 GDN, 2 IGDN
   int8_t dy[kMaxTaps], dx[kMaxTaps];
@@ -158,7 +158,7 @@ __device__ __forceinline__ Pack8 split8(const float *v) {
   return p;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[4];
   __shared__ __align__(8) uint64_t empty_bar[4];
@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int64_t pix = ok ? ((static_cast<int64_t>(n_img) * p.H + iy) * p.W + ix) : 0;
       const __nv_bfloat16 *gh = p.a_hi + pix * p.Cin + kc * kBK;
       const __nv_bfloat16 *gl = p.a_lo + pix * p.Cin + kc * kBK;
-      const int kleft = p.Cin - kc * kBK;  // valid k elements in this chunk (may be < 64 on the tail)
+      const int kleft = p.Cin - kc * kBK;  // valid k elements in this chunk (may be < kBK on the tail)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < kBK / 8; ++c) {
         const uint32_t nbytes = (ok && c * 8 < kleft) ? 16u : 0u;
         const uint32_t so = static_cast<uint32_t>(c) * (kBM * 16u) + row_off;
         cp_async16(sa + so, nbytes ? static_cast<const void *>(gh + c * 8) : static_cast<const void *>(p.a_hi), nbytes);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
     if (fuse_gdn) {
       // ---- fused GDN, part 1: turn the accumulator into the A operand of the second GEMM.
-      // x = acc + bias; x^2 is split into bf16 planes and written, 64 channels (one k-step) at a time, into the
+      // x = acc + bias; x^2 is split into bf16 planes and written, kBK channels (one k-step) at a time, into the
       // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
       for (int g = 0; g < gdn_ksteps; ++g) {
         const int ks = ksteps + g;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
         }
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < kBK / 8; ++c) {
           const int col = g * kBK + c * 8;
           uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
           if (col < BN) {  // warp-uniform
@@ -591,8 +591,10 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
     p.dx[t] = d->dx[t];
   }
   const size_t stage_bytes = 2 * (kBM * kBK * 2) + 2 * static_cast<size_t>(d->BN) * kBK * 2;
-  int stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes);
+  // two CTAs per SM (one CTA's epilogue overlaps the other's main loop): each gets half of the shared memory
+  int stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) / 2 - 2048) / stage_bytes);
   if (stages > 4) stages = 4;
+  if (stages < 2) stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes) >= 2 ? 2 : stages;
   const int ksteps = p.ntaps * p.kchunks;
   if (stages > ksteps) stages = ksteps < 2 ? 2 : ksteps;
   CAI_CHECK_ARG(stages >= 2, "cai_conv_gemm: tile does not fit shared memory");

@@ -31,7 +31,7 @@ from torch import Tensor
 from . import _lib
 from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, ConvDesc, check, current_stream, lib, ptr, require_cuda
 
-_BK = 64
+_BK = 32
 
 
 class Conv2d(nn.Module):
@@ -169,14 +169,14 @@ def _choose_bn(cout: int) -> int:
 
 
 def pack_weights(w_taps: Tensor, bn: int) -> Tensor:
-    """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][T * kchunks][hi | lo][BN x 64 bf16] in the UMMA canonical
+    """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][T * kchunks][hi | lo][BN x 32 bf16] in the UMMA canonical
     K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2)."""
     T, cout, cin = w_taps.shape
     nt = (cout + bn - 1) // bn
     kc = (cin + _BK - 1) // _BK
     wp = torch.zeros((T, nt * bn, kc * _BK), dtype=torch.float32, device=w_taps.device)
     wp[:, :cout, :cin] = w_taps
-    wp = wp.view(T, nt, bn // 8, 8, kc, 8, 8).permute(1, 0, 4, 5, 2, 3, 6)  # nt, T, kc, k8, r8, r%8, k%8
+    wp = wp.view(T, nt, bn // 8, 8, kc, _BK // 8, 8).permute(1, 0, 4, 5, 2, 3, 6)  # nt, T, kc, k8, r8, r%8, k%8
     hi = wp.to(torch.bfloat16)
     lo = (wp - hi.float()).to(torch.bfloat16)
     packed = torch.stack([hi, lo], dim=3).contiguous()  # nt, T, kc, 2, k8, r8, r%8, k%8
