@@ -165,8 +165,10 @@ def strings_to_device(strings: Sequence[bytes], device) -> tuple:
 
 
 def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, state: Optional[torch.Tensor] = None,
-           resume: bool = False, device_words=None) -> torch.Tensor:
-    """Decode B strings; ``indexes`` int32 [B, n] in coder order.  Returns int32 [B, n]."""
+           resume: bool = False, device_words=None, status_out: Optional[list] = None) -> torch.Tensor:
+    """Decode B strings; ``indexes`` int32 [B, n] in coder order.  Returns int32 [B, n].
+    With ``status_out`` (a list) the per-string status tensor is appended instead of being checked here, so the call
+    stays asynchronous (the pinned staging buffer is kept alive by torch's caching host allocator)."""
     require_cuda(indexes, "indexes")
     assert indexes.dtype == torch.int32 and indexes.is_contiguous()
     B = int(indexes.size(0)) if indexes.dim() > 0 else 0
@@ -189,8 +191,15 @@ def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, sta
         check(lib().cai_rans_decode_batch(table.handle, ptr(words), ptr(wb), ptr(wcount), ptr(indexes), None, n, B, ptr(out),
                                           ptr(state), 1 if resume else 0, ptr(status), current_stream()),
               "cai_rans_decode_batch")
-    if keep is not None:
-        # the pinned staging buffer must outlive the async H2D copy
+    if status_out is not None:
+        status_out.append(status)
+    elif keep is not None:
         torch.cuda.current_stream(dev).synchronize()
         _raise_status(status, "rANS decode")
     return out
+
+
+def check_status(statuses, what="rANS decode"):
+    """Deferred check of the status tensors collected with ``status_out`` (synchronises)."""
+    for st in statuses:
+        _raise_status(st, what)

@@ -268,7 +268,7 @@ class ScaleHyperprior(CompressionModel):
         return {"strings": [ys, zs], "shape": out["shape"]}
 
     @torch.no_grad()
-    def _decompress_chunks(self, chunks, shape, device):
+    def _decompress_chunks(self, chunks, shape, device, statuses=None):
         """chunks: list of (coder_stream, y_words, z_words, n) with *_words = (strings | None, device_words | None)."""
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         eb_t, gc_t = eb._table(), gc._table()
@@ -287,7 +287,7 @@ class ScaleHyperprior(CompressionModel):
             with torch.cuda.stream(ck):
                 ck.wait_event(ready)
                 z_idx = kernels.channel_indexes(n, C, h * w, device)
-                z_sym = coder.decode(eb_t, z_words[0], z_idx, device_words=z_words[1])
+                z_sym = coder.decode(eb_t, z_words[0], z_idx, device_words=z_words[1], status_out=statuses)
                 self._handoff(syn, z_sym)
             with torch.cuda.stream(syn):
                 z_hat = kernels.dequantize(z_sym, None, eb._get_medians(), (n, C, h, w), _CL)
@@ -295,7 +295,7 @@ class ScaleHyperprior(CompressionModel):
                 _, y_idx = kernels.gc_quantize_index(None, scales_hat, None, gc.scale_table, gc._bound_scale())
                 self._handoff(ck, y_idx)
             with torch.cuda.stream(ck):
-                y_sym = coder.decode(gc_t, y_words[0], y_idx, device_words=y_words[1])
+                y_sym = coder.decode(gc_t, y_words[0], y_idx, device_words=y_words[1], status_out=statuses)
                 done = ck.record_event()  # "syn" must NOT wait here: that would serialise the chunks' decodes
                 y_sym.record_stream(syn)
             pending.append((y_sym, means_hat, tuple(scales_hat.shape), done))
@@ -326,7 +326,11 @@ class ScaleHyperprior(CompressionModel):
         for k, i in enumerate(starts):
             ys, zs = list(strings[0][i:i + self.micro_batch]), list(strings[1][i:i + self.micro_batch])
             chunks.append((S["coder"][k % len(S["coder"])], (ys, None), (zs, None), len(ys)))
-        return self._decompress_chunks(chunks, shape, dev)
+        statuses = []
+        out = self._decompress_chunks(chunks, shape, dev, statuses)
+        torch.cuda.current_stream(dev).synchronize()  # one sync per call: surface decoder errors like the reference would
+        coder.check_status(statuses)
+        return out
 
     @torch.no_grad()
     def decompress_from_device(self, enc, shape):
@@ -336,7 +340,7 @@ class ScaleHyperprior(CompressionModel):
         for ye, ze in zip(y_encs, z_encs):
             with torch.cuda.stream(ye.stream):  # the word offsets are derived from n_words on the coder stream
                 chunks.append((ye.stream, (None, ye.device_words()), (None, ze.device_words()), int(ye.n_words.numel())))
-        return self._decompress_chunks(chunks, shape, dev)
+        return self._decompress_chunks(chunks, shape, dev, [])
 
 
 class MeanScaleHyperprior(ScaleHyperprior):
