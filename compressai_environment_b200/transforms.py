@@ -33,6 +33,10 @@ from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, ConvDesc, check, current_str
 
 _BK = 32
 
+# Optional profiling hook used by bench.py (same convention as coder.TIMING): when set to a dict, every
+# cai_conv_gemm launch appends a (start, end) CUDA-event pair recorded on the launching stream.
+TIMING = None
+
 
 class Conv2d(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=5, stride=2, padding=None):
@@ -297,7 +301,13 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
     for t, (dy, dx) in enumerate(taps):
         d.dy[t], d.dx[t] = dy, dx
     with torch.cuda.device(a.hi.device):
+        if TIMING is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib().cai_conv_gemm(d, current_stream()), "cai_conv_gemm")
+        if TIMING is not None:
+            e1.record()
+            TIMING.setdefault("conv_gemm_kernel", []).append((e0, e1))
 
 
 _ACT = {None: 0, "relu": 1, "leaky": 2}
