@@ -78,6 +78,10 @@ SIGNATURES = {
     "cai_split_planes": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cai_im2col_split": (c_int, [c_void_p] + [c_int32] * 11 + [c_void_p, c_void_p, c_void_p]),
     "cai_col2im": (c_int, [c_void_p, c_void_p] + [c_int32] * 11 + [c_float, c_float, c_void_p, c_void_p]),
+    "cai_gdn_bwd_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "cai_gdn_bwd_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "cai_gdn_bwd_params": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -116,7 +120,8 @@ KERNELS_PER_CALL = {"cai_table_create": 3, "cai_rans_encode_batch": 1, "cai_rans
                     "cai_rans_decode_batch": 1, "cai_gc_quantize_index": 1, "cai_eb_quantize_index": 1,
                     "cai_dequantize": 1, "cai_pmf_to_quantized_cdf": 1, "cai_gc_forward": 1, "cai_gc_backward": 1,
                     "cai_eb_forward": 1, "cai_eb_backward": 1, "cai_eb_logits": 1, "cai_conv_gemm": 1,
-                    "cai_split_planes": 1, "cai_im2col_split": 1, "cai_col2im": 1}
+                    "cai_split_planes": 1, "cai_im2col_split": 1, "cai_col2im": 1, "cai_gdn_bwd_prepare": 1,
+                    "cai_gdn_bwd_finish": 1, "cai_gdn_bwd_params": 1}
 LAUNCHES = 0
 
 

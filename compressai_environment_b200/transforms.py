@@ -511,10 +511,81 @@ def _true_out_channels(mods):
     return None
 
 
+def _nhwc_padded(x: Tensor, cp: int) -> Tensor:
+    """logical NCHW fp32 -> contiguous [N, H, W, cp] (zero padded channels)."""
+    xn = x.detach().float().permute(0, 2, 3, 1)
+    if cp != xn.size(3):
+        xn = F.pad(xn, (0, cp - xn.size(3)))
+    return xn.contiguous()
+
+
+def _planes_of(xn: Tensor) -> Planes:
+    N, H, W, C = xn.shape
+    out = Planes.empty(N, H, W, C, xn.device)
+    with torch.cuda.device(xn.device):
+        check(lib().cai_split_planes(ptr(xn), CAI_LAYOUT_NHWC, N, C, H * W, C, ptr(out.hi), ptr(out.lo), current_stream()),
+              "cai_split_planes")
+    return out
+
+
+class _GDNFunction(torch.autograd.Function):
+    """GDN / IGDN with both directions on this package's kernels (training mode): forward = 1x1 tcgen05 GEMM of x^2
+    with gamma + fused finalize; backward = norm GEMM, elementwise stage, gamma^T GEMM, elementwise stage, and the
+    pixel-reduction outer product for dgamma / dbeta (cai_gdn_bwd_*; formulas SURVEY.md Appendix D.1)."""
+
+    @staticmethod
+    def forward(ctx, x, beta, gamma, inverse):
+        require_cuda(x, "inputs")
+        C = x.size(1)
+        cp = _c16(C)
+        bn = _choose_bn(cp)
+        if bn != cp:
+            raise _lib.CaiError("GDN with more than 256 channels is not supported by the fused kernel")
+        xn = _nhwc_padded(x, cp)
+        N, H, W, _ = xn.shape
+        g_packed = pack_weights(_pad_taps(gamma.detach().float().reshape(1, C, C), cp, cp), bn)
+        b_pad = _pad_vec(beta, cp, 1.0)
+        xp, sq = _planes_of(xn), _planes_of(xn * xn)
+        out = torch.empty((N, H, W, cp), dtype=torch.float32, device=xn.device)
+        _launch(sq, g_packed, b_pad, [(0, 0)], bn, cp, H, W, H, W, 1, 0, 0, 1, 4 if inverse else 3, xp, out, None, None,
+                None)
+        ctx.save_for_backward(xn, gamma.detach(), beta.detach())
+        ctx.cfg = (bool(inverse), C, cp, bn)
+        return out[..., :C].permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        xn, gamma, beta = ctx.saved_tensors
+        inverse, C, cp, bn = ctx.cfg
+        N, H, W, _ = xn.shape
+        dev = xn.device
+        gn = _nhwc_padded(g, cp)
+        gam = _pad_taps(gamma.float().reshape(1, C, C), cp, cp)
+        b_pad = _pad_vec(beta, cp, 1.0)
+        sq = _planes_of(xn * xn)
+        norm = torch.empty_like(xn)
+        _launch(sq, pack_weights(gam, bn), b_pad, [(0, 0)], bn, cp, H, W, H, W, 1, 0, 0, 1, 0, None, norm, None, None, None)
+        t = torch.empty_like(xn)
+        p = torch.empty_like(xn)
+        tp = Planes.empty(N, H, W, cp, dev)
+        n_el = xn.numel()
+        with torch.cuda.device(dev):
+            check(lib().cai_gdn_bwd_prepare(ptr(xn), ptr(norm), ptr(gn), int(inverse), n_el, ptr(t), ptr(tp.hi), ptr(tp.lo),
+                                            ptr(p), current_stream()), "cai_gdn_bwd_prepare")
+        u = torch.empty_like(xn)
+        _launch(tp, pack_weights(gam.transpose(1, 2).contiguous(), bn), None, [(0, 0)], bn, cp, H, W, H, W, 1, 0, 0, 1, 0,
+                None, u, None, None, None)
+        gx = torch.empty_like(xn)
+        g_beta = torch.empty(cp, dtype=torch.float32, device=dev)
+        g_gamma = torch.empty((cp, cp), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().cai_gdn_bwd_finish(ptr(p), ptr(xn), ptr(u), int(inverse), n_el, ptr(gx), current_stream()),
+                  "cai_gdn_bwd_finish")
+            check(lib().cai_gdn_bwd_params(ptr(t), ptr(xn), N * H * W, cp, int(inverse), ptr(g_beta), ptr(g_gamma),
+                                           current_stream()), "cai_gdn_bwd_params")
+        return gx[..., :C].permute(0, 3, 1, 2), g_beta[:C], g_gamma[:C, :C], None
+
+
 def gdn(x, beta, gamma, inverse):
-    """Functional GDN used by ``layers.GDN.forward`` in training mode (autograd through torch ops)."""
-    require_cuda(x, "inputs")
-    C = x.size(1)
-    norm = F.conv2d(x * x, gamma.reshape(C, C, 1, 1), beta)
-    norm = torch.sqrt(norm) if inverse else torch.rsqrt(norm)
-    return x * norm
+    """Functional GDN used by ``layers.GDN.forward`` in training mode: forward and backward on our kernels."""
+    return _GDNFunction.apply(x, beta, gamma, bool(inverse))

@@ -272,6 +272,21 @@ int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, in
                int32_t Wo, int32_t ksize, int32_t stride, int32_t pad, int32_t Npad, int32_t out_layout, float clamp_lo,
                float clamp_hi, float *out, cai_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GDN / IGDN backward (training mode; forward: compressai/layers/gdn.py:77-92, formulas: SURVEY.md Appendix D.1).
+ * NHWC fp32 tensors of n = P * C elements.  The two channel-mixing products (norm = gamma . x^2 + beta and
+ * u = gamma^T t) are cai_conv_gemm calls; these entry points are the stages around them:
+ *   prepare: t = g x norm^(-3/2) (GDN) / g x norm^(-1/2) (IGDN), as fp32 and split planes; p = g norm^(-/+ 1/2)
+ *   finish : dx = p - x u (GDN) / p + x u (IGDN)
+ *   params : dbeta[i] = s sum_pix t_i, dgamma[i][j] = s sum_pix t_i x_j^2, s = -1/2 (GDN) / +1/2 (IGDN)  (overwrites)
+ * ---------------------------------------------------------------------------------------------- */
+int cai_gdn_bwd_prepare(const float *x, const float *norm, const float *g, int32_t inverse, int64_t n, float *t,
+                        void *t_hi, void *t_lo, float *p, cai_stream_t stream);
+int cai_gdn_bwd_finish(const float *p, const float *x, const float *u, int32_t inverse, int64_t n, float *gx,
+                       cai_stream_t stream);
+int cai_gdn_bwd_params(const float *t, const float *x, int64_t P, int32_t C, int32_t inverse, float *g_beta,
+                       float *g_gamma, cai_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

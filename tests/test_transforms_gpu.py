@@ -131,3 +131,47 @@ def test_full_stack_matches_torch():
                       padding=2)
     _check(y, r, 5e-4)
     _check(z, rz, 5e-4)
+
+
+def test_gdn_backward_golden(golden):
+    """GDN / IGDN forward + backward (through the non-negative reparametrisation) vs the reference autograd fixture."""
+    from compressai_environment_b200.layers import GDN
+
+    f = golden("fp")
+    for tag, inv in (("gdn", False), ("igdn", True)):
+        m = GDN(8, inverse=inv).to(DEV)
+        with torch.no_grad():
+            m.beta.copy_(torch.from_numpy(f[tag + "_beta"]))
+            m.gamma.copy_(torch.from_numpy(f[tag + "_gamma"]))
+        x = torch.from_numpy(f[tag + "_x"]).to(DEV).requires_grad_()
+        y = m(x)
+        _check(y, torch.from_numpy(f[tag + "_y"]).to(DEV))
+        y.backward(torch.from_numpy(f[tag + "_gout"]).to(DEV))
+        _check(x.grad, torch.from_numpy(f[tag + "_gx"]).to(DEV), 5e-4)
+        _check(m.beta.grad, torch.from_numpy(f[tag + "_gbeta"]).to(DEV), 5e-4)
+        _check(m.gamma.grad, torch.from_numpy(f[tag + "_ggamma"]).to(DEV), 5e-4)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_backward_vs_torch_autograd(inverse):
+    from compressai_environment_b200.layers import GDN
+
+    torch.manual_seed(7)
+    C = 128
+    m = GDN(C, inverse=inverse).to(DEV)
+    with torch.no_grad():
+        m.beta.add_(0.2 * torch.rand_like(m.beta))
+        m.gamma.add_(0.05 * torch.rand_like(m.gamma))
+    x = (torch.randn(2, C, 9, 11, device=DEV) * 2).requires_grad_()
+    go = torch.randn(2, C, 9, 11, device=DEV)
+    m(x).backward(go)
+    got = (x.grad.clone(), m.beta.grad.clone(), m.gamma.grad.clone())
+    x.grad = None
+    m.zero_grad()
+    beta, gamma = m.effective_params()
+    xd = x.double()
+    norm = F.conv2d(xd * xd, gamma.double().reshape(C, C, 1, 1), beta.double())
+    (xd * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))).backward(go.double())
+    _check(got[0], x.grad, 5e-4)
+    _check(got[1], m.beta.grad, 5e-4)
+    _check(got[2], m.gamma.grad, 5e-4)
