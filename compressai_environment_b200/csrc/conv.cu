@@ -26,15 +26,21 @@
 // 128 lanes x BN columns of TMEM, drained with tcgen05.ld.32x32b.x16.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cai {
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
 constexpr int kBK = 32;           // k elements per stage (2 x UMMA_K=16): small stages -> 2 CTAs per SM
-constexpr int kProducerThreads = 128;
+constexpr int kProducerThreads = 64;   // warps 0-1 issue the A-tile cp.async copies (fewer mbarrier arrivals per k-step)
+constexpr int kLoadIters = 8;          // rows per producer thread: kBM / (kProducerThreads / 4)
 constexpr int kConvThreads = 160;
 constexpr int kMaxTaps = 32;
+// A-tile chunk pitch (UMMA leading byte offset): 128 rows x 16 B + 32 B of padding so that a quarter warp that
+// writes 2 pixels x 4 k-chunks touches 8 distinct 16-byte bank groups ((2c + p) mod 8) -> conflict-free LDGSTS
+constexpr uint32_t kLboA = kBM * 16u + 32u;
 constexpr uint32_t kSpinLimit = 1u << 28;
 
 struct ConvKernelParams {
@@ -60,6 +66,7 @@ struct ConvKernelParams {
   const unsigned char *gdn_w;        // packed gamma: [kc][hi | lo][BN x kBK bf16], NULL = no fusion
   const float *gdn_beta;             // [Cout]
   int gdn_mode;                      // 1 GDN, 2 IGDN
+  int debug;                         // experiment bitmask: 1 skip A loads, 2 skip B loads, 4 skip MMAs
   int8_t dy[kMaxTaps], dx[kMaxTaps];
 };
 
@@ -85,7 +92,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   const int warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN;
   const int stages = p.stages;
-  const uint32_t a_plane = kBM * kBK * 2;          // 16 KB: one bf16 plane of the A tile
+  const uint32_t a_plane = (kBK / 8) * kLboA;      // one bf16 plane of the A tile: kBK/8 chunks of kLboA bytes
   const uint32_t b_plane = static_cast<uint32_t>(BN) * kBK * 2;
   const uint32_t stage_bytes = 2 * a_plane + 2 * b_plane;
   const int ksteps = p.ntaps * p.kchunks;
@@ -206,61 +213,114 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   const uint32_t tmem_base = s_tmem_base;
 
   if (warp < 4) {
-    // ===================== producers: thread = pixel row of the tile =====================
+    // ===================== producers =====================
+    // Load mapping: 4 lanes share one pixel (its kBK = 32 channels = 64 contiguous bytes per plane), a warp
+    // instruction covers 8 pixels -> 8 L1 wavefronts per LDGSTS instead of 32 with a lane-per-pixel mapping.
+    // Thread (warp w, lane l) loads chunk c = l & 3 of rows it * 32 + w * 8 + (l >> 2), it = 0..3.
+    // The epilogue below keeps thread = TMEM lane = row `tid`.
     const int r = tid;
     const int64_t m = m0 + r;
     const bool row_ok = m < M_total;
     int n_img = 0, pi = 0, pj = 0;
-    if (row_ok) {
+    {
       const int64_t per = static_cast<int64_t>(p.Hp) * p.Wp;
-      n_img = static_cast<int>(m / per);
-      const int rem = static_cast<int>(m - n_img * per);
-      pi = rem / p.Wp;
-      pj = rem - pi * p.Wp;
+      if (row_ok) {
+        n_img = static_cast<int>(m / per);
+        const int rem = static_cast<int>(m - n_img * per);
+        pi = rem / p.Wp;
+        pj = rem - pi * p.Wp;
+      }
     }
     const uint32_t row_off = (static_cast<uint32_t>(r) >> 3) * 128u + (static_cast<uint32_t>(r) & 7u) * 16u;
     const unsigned char *wbase = p.w_packed + static_cast<size_t>(n_tile) * ksteps * (2 * b_plane);
 
-    auto issue = [&](int ks) {
-      const int s = ks % stages;
-      const int t = ks / p.kchunks, kc = ks - t * p.kchunks;
-      unsigned char *sa = smem + static_cast<size_t>(s) * stage_bytes;
-      const int iy = pi * p.is + p.dy[t], ix = pj * p.is + p.dx[t];
-      const bool ok = row_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      const int64_t pix = ok ? ((static_cast<int64_t>(n_img) * p.H + iy) * p.W + ix) : 0;
-      const __nv_bfloat16 *gh = p.a_hi + pix * p.Cin + kc * kBK;
-      const __nv_bfloat16 *gl = p.a_lo + pix * p.Cin + kc * kBK;
-      const int kleft = p.Cin - kc * kBK;  // valid k elements in this chunk (may be < kBK on the tail)
+    const int lc = lane & 3;  // k-chunk handled by this lane
+    const bool is_loader = warp < kProducerThreads / 32;
+    int ld_iy[kLoadIters], ld_ix[kLoadIters];  // input coordinate of tap (0, 0) for the rows this thread loads
+    int64_t ld_img[kLoadIters];                // image base pixel index
+    uint32_t ld_so[kLoadIters];
 #pragma unroll
-      for (int c = 0; c < kBK / 8; ++c) {
-        const uint32_t nbytes = (ok && c * 8 < kleft) ? 16u : 0u;
-        const uint32_t so = static_cast<uint32_t>(c) * (kBM * 16u) + row_off;
-        cp_async16(sa + so, nbytes ? static_cast<const void *>(gh + c * 8) : static_cast<const void *>(p.a_hi), nbytes);
-        cp_async16(sa + a_plane + so, nbytes ? static_cast<const void *>(gl + c * 8) : static_cast<const void *>(p.a_lo),
-                   nbytes);
+    for (int it = 0; it < kLoadIters; ++it) {
+      const int lr = it * (kProducerThreads / 4) + (warp & (kProducerThreads / 32 - 1)) * 8 + (lane >> 2);
+      const int64_t lm = m0 + lr;
+      ld_so[it] = static_cast<uint32_t>(lc) * kLboA + (static_cast<uint32_t>(lr) >> 3) * 128u +
+                  (static_cast<uint32_t>(lr) & 7u) * 16u;
+      if (lm < M_total) {
+        const int64_t per = static_cast<int64_t>(p.Hp) * p.Wp;
+        const int ni = static_cast<int>(lm / per);
+        const int rem = static_cast<int>(lm - ni * per);
+        const int li = rem / p.Wp;
+        ld_iy[it] = li * p.is;
+        ld_ix[it] = (rem - li * p.Wp) * p.is;
+        ld_img[it] = static_cast<int64_t>(ni) * p.H * p.W;
+      } else {
+        ld_iy[it] = -(1 << 28);
+        ld_ix[it] = 0;
+        ld_img[it] = 0;
+      }
+    }
+
+    // Per-tap state (recomputed only when the tap changes, i.e. every kchunks k-steps): element offset of the
+    // tap's input pixel for each of the 4 rows, 0 / 16 byte count for padding.  Per k-step only the channel chunk
+    // offset (kc * kBK elements) is added, so the steady-state cost is a handful of instructions per cp.async.
+    int64_t tap_off[kLoadIters];
+    uint32_t tap_bytes[kLoadIters];
+    int cur_t = 0, cur_kc = 0;
+    auto set_tap = [&](int t) {
+      const int dy = p.dy[t], dx = p.dx[t];
+#pragma unroll
+      for (int it = 0; it < kLoadIters; ++it) {
+        const int iy = ld_iy[it] + dy, ix = ld_ix[it] + dx;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        tap_off[it] = ok ? ((ld_img[it] + static_cast<int64_t>(iy) * p.W + ix) * p.Cin + lc * 8) : 0;
+        tap_bytes[it] = ok ? 16u : 0u;
+      }
+    };
+    set_tap(0);
+
+    auto issue = [&](int ks, int s) {  // must be called with ks = 0, 1, 2, ... in order; s = ks mod stages
+      unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
+      const int kbase = cur_kc * kBK;
+      const bool k_ok = kbase + lc * 8 < p.Cin;
+#pragma unroll
+      for (int it = 0; it < kLoadIters; ++it) {
+        if (p.debug & 1) break;
+        const uint32_t nbytes = k_ok ? tap_bytes[it] : 0u;
+        const int64_t off = nbytes ? tap_off[it] + kbase : 0;
+        cp_async16(sa + ld_so[it], p.a_hi + off, nbytes);
+        cp_async16(sa + a_plane + ld_so[it], p.a_lo + off, nbytes);
       }
       if (tid == 0) {
-        mbar_expect_tx(&full_bar[s], 2 * b_plane);
-        tma_bulk_g2s(sa + 2 * a_plane, wbase + static_cast<size_t>(ks) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
+        if (p.debug & 2) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_expect_tx(&full_bar[s], 2 * b_plane);
+          tma_bulk_g2s(sa + 2 * a_plane, wbase + static_cast<size_t>(ks) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
+        }
+      }
+      if (++cur_kc == p.kchunks) {
+        cur_kc = 0;
+        if (++cur_t < p.ntaps) set_tap(cur_t);
       }
     };
 
-    // software pipeline: keep (stages - 1) k-steps of cp.async in flight
-    const int lag = stages - 1;
-    for (int ks = 0; ks < ksteps + lag; ++ks) {
-      if (ks < ksteps) {
-        const int s = ks % stages;
-        if (ks >= stages) mbar_wait_bounded(&empty_bar[s], ((ks / stages) - 1) & 1);
-        issue(ks);
-      }
-      cp_async_commit();
-      if (ks >= lag) {
-        // k-step (ks - lag) has landed for this thread
-        if (lag == 1) cp_async_wait<1>();
-        else if (lag == 2) cp_async_wait<2>();
-        else cp_async_wait<3>();
-        fence_async_proxy();
-        mbar_arrive(&full_bar[(ks - lag) % stages]);
+    // Producer loop.  Each thread's cp.async copies of a k-step are tied to the stage's "full" mbarrier with
+    // cp.async.mbarrier.arrive.noinc: the hardware performs this thread's arrival when its copies have landed, so
+    // the thread never waits for its own loads and runs up to `stages` k-steps ahead of the MMA warp (the only
+    // blocking point is the "empty" barrier of the stage being refilled).  Ring positions and parities are carried
+    // incrementally.
+    int ps = 0, ppass = 0;  // stage of k-step ks, number of completed passes over the ring
+    if (!is_loader) {       // warps 2-3 only take part in the epilogue: fast-forward their ring position
+      ppass = ksteps / stages;
+      ps = ksteps - ppass * stages;
+    }
+    for (int ks = 0; is_loader && ks < ksteps; ++ks) {
+      if (ppass > 0) mbar_wait_bounded(&empty_bar[ps], (ppass - 1) & 1);
+      issue(ks, ps);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[ps])) : "memory");
+      if (++ps == stages) {
+        ps = 0;
+        ++ppass;
       }
     }
 
@@ -273,10 +333,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       // x = acc + bias; x^2 is split into bf16 planes and written, kBK channels (one k-step) at a time, into the
       // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
       for (int g = 0; g < gdn_ksteps; ++g) {
-        const int ks = ksteps + g;
-        const int s = ks % stages;
-        if (ks >= stages) mbar_wait_bounded(&empty_bar[s], ((ks / stages) - 1) & 1);
-        unsigned char *sa = smem + static_cast<size_t>(s) * stage_bytes;
+        const int s = ps;
+        if (ppass > 0) mbar_wait_bounded(&empty_bar[s], (ppass - 1) & 1);
+        if (++ps == stages) {
+          ps = 0;
+          ++ppass;
+        }
+        unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
         if (tid == 0) {
           mbar_expect_tx(&full_bar[s], 2 * b_plane);
           tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
@@ -299,12 +362,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             vh = pk.hi;
             vl = pk.lo;
           }
-          const uint32_t so = static_cast<uint32_t>(c) * (kBM * 16u) + row_off;
+          const uint32_t so = static_cast<uint32_t>(c) * kLboA + row_off;
           *reinterpret_cast<uint4 *>(sa + so) = vh;
           *reinterpret_cast<uint4 *>(sa + a_plane + so) = vl;
         }
         fence_async_proxy();
-        mbar_arrive(&full_bar[s]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // all four epilogue warps have written (and fenced) their rows
+        if (is_loader) mbar_arrive(&full_bar[s]);     // same arrival count as a main-loop k-step
       }
       mbar_wait_bounded(&acc2_bar, 0);
       tc_fence_after();
@@ -405,19 +469,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                            (static_cast<uint32_t>(kBM >> 4) << 24);
-    const uint32_t lbo_a = kBM * 16u, lbo_b = static_cast<uint32_t>(BN) * 16u;
+    const uint32_t lbo_a = kLboA, lbo_b = static_cast<uint32_t>(BN) * 16u;
+    int s = 0;
+    uint32_t mphase = 0;
     for (int ks = 0; ks < ksteps + gdn_ksteps; ++ks) {
-      const int s = ks % stages;
-      mbar_wait_bounded(&full_bar[s], (ks / stages) & 1);
+      mbar_wait_bounded(&full_bar[s], mphase);
       tc_fence_after();
       if (lane == 0) {
         const bool second = ks >= ksteps;  // GDN GEMM: A = x^2 planes written by the epilogue warps, B = gamma
         const uint32_t d_tmem = second ? tmem_base + acc_cols : tmem_base;
         const int first_ks = second ? ksteps : 0;
-        const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t sa = smem_u32(smem) + static_cast<uint32_t>(s) * stage_bytes;
         const uint32_t a_hi = sa, a_lo = sa + a_plane, b_hi = sa + 2 * a_plane, b_lo = b_hi + b_plane;
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {
+          if (p.debug & 4) break;
           const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, 128);
           const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, 128);
           const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
@@ -431,6 +497,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         if (second && ks == ksteps + gdn_ksteps - 1) umma_commit(&acc2_bar);  // norm accumulator complete
       }
       __syncwarp();
+      if (++s == stages) {
+        s = 0;
+        mphase ^= 1u;
+      }
     }
   }
 
@@ -590,11 +660,17 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
     p.dy[t] = d->dy[t];
     p.dx[t] = d->dx[t];
   }
-  const size_t stage_bytes = 2 * (kBM * kBK * 2) + 2 * static_cast<size_t>(d->BN) * kBK * 2;
+  const size_t stage_bytes = 2 * static_cast<size_t>((kBK / 8) * kLboA) + 2 * static_cast<size_t>(d->BN) * kBK * 2;
   // two CTAs per SM (one CTA's epilogue overlaps the other's main loop): each gets half of the shared memory
   int stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) / 2 - 2048) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes) >= 2 ? 2 : stages;
+  if (const char *ov = getenv("CAI_CONV_STAGES")) {  // tuning override (experiments only)
+    const int v = atoi(ov);
+    const int cap = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes);
+    if (v >= 2) stages = v < cap ? v : cap;
+    if (stages > 4) stages = 4;
+  }
   const int ksteps = p.ntaps * p.kchunks;
   if (stages > ksteps) stages = ksteps < 2 ? 2 : ksteps;
   CAI_CHECK_ARG(stages >= 2, "cai_conv_gemm: tile does not fit shared memory");
@@ -602,6 +678,7 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   p.gdn_w = static_cast<const unsigned char *>(d->gdn_w);
   p.gdn_beta = d->gdn_beta;
   p.gdn_mode = d->gdn_mode;
+  if (const char *dbg = getenv("CAI_CONV_DEBUG")) p.debug = atoi(dbg);
   if (p.gdn_w) {
     CAI_CHECK_ARG(d->BN == d->Cout && d->BN <= 256, "cai_conv_gemm: fused GDN needs all channels in one tile (Cout <= 256)");
     CAI_CHECK_ARG(d->gdn_beta && (d->gdn_mode == 1 || d->gdn_mode == 2), "cai_conv_gemm: fused GDN needs beta and mode 1|2");
