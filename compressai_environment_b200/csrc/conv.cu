@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
       uint32_t raw2[16];
       if (fuse_gdn) tmem_ld16(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
-      if (!row_ok) continue;
+      if (!row_ok || (p.debug & 8)) continue;
       const int cg = n0 + c0;  // global output channel of raw[0]
       if (cg >= p.Cout) continue;
       float v[16];
@@ -535,31 +535,40 @@ split_planes_kernel(const float *__restrict__ x, int layout, int64_t N, int64_t 
 
 // im2col for tiny Cin (first layer, Cin = 3): [N, H, W, C] fp32 (any layout) -> split planes [N*Ho*Wo, Kpad]
 // with k = (ky * ks + kx) * C + c, zero padded to Kpad.
+// One thread = one output pixel x one group of 8 k-values -> one 16-byte store per plane (coalesced along k).
 __global__ void __launch_bounds__(256)
 im2col_split_kernel(const float *__restrict__ x, int layout, int N, int C, int H, int W, int Ho, int Wo, int ksz,
                     int stride, int pad, int Kpad, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
-  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * Kpad;
+  const int groups = Kpad >> 3;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * groups;
   const int64_t gs = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int K = ksz * ksz * C;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += gs) {
-    const int k = static_cast<int>(i % Kpad);
-    const int64_t pix = i / Kpad;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % C, t = k / C, ky = t / ksz, kx = t - ky * ksz;
-      const int ox = static_cast<int>(pix % Wo);
-      const int64_t r = pix / Wo;
-      const int oy = static_cast<int>(r % Ho), n = static_cast<int>(r / Ho);
-      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        v = (layout == CAI_LAYOUT_NHWC) ? x[((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c]
-                                        : x[((static_cast<int64_t>(n) * C + c) * H + iy) * W + ix];
+    const int g = static_cast<int>(i % groups);
+    const int64_t pix = i / groups;
+    const int ox = static_cast<int>(pix % Wo);
+    const int64_t r = pix / Wo;
+    const int oy = static_cast<int>(r % Ho), n = static_cast<int>(r / Ho);
+    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int t = k / C, c = k - t * C;
+        const int ky = t / ksz, kx = t - ky * ksz;
+        const int iy = iy0 + ky, ix = ix0 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          val = (layout == CAI_LAYOUT_NHWC) ? __ldg(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c)
+                                            : __ldg(x + ((static_cast<int64_t>(n) * C + c) * H + iy) * W + ix);
+        }
       }
+      v[j] = val;
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    const Pack8 pk = split8(v);
+    *reinterpret_cast<uint4 *>(hi + pix * Kpad + g * 8) = pk.hi;
+    *reinterpret_cast<uint4 *>(lo + pix * Kpad + g * 8) = pk.lo;
   }
 }
 
@@ -715,7 +724,7 @@ int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32
   DeviceProps dp;
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
-  im2col_split_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * Kpad), 256, 0,
+  im2col_split_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8)), 256, 0,
                         static_cast<cudaStream_t>(stream_)>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad,
                                                               static_cast<__nv_bfloat16 *>(hi),
                                                               static_cast<__nv_bfloat16 *>(lo));

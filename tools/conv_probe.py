@@ -6,16 +6,18 @@ from compressai_environment_b200.layers import GDN
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 kind = sys.argv[2] if len(sys.argv) > 2 else "conv"
 dev = "cuda"; torch.manual_seed(0)
-if kind == "conv":
+if kind == "conv1":
+    mods = [Conv2d(3, 128).to(dev), GDN(128).to(dev)]; x = torch.rand(B, 3, 512, 768, device=dev); macs = B * 256 * 384 * (128 * 75 + 128 * 128)
+elif kind == "conv":
     mods = [Conv2d(128, 128).to(dev), GDN(128).to(dev)]; x = torch.randn(B, 128, 256, 384, device=dev); macs = B * 128 * 192 * (128 * 128 * 25 + 128 * 128)
 else:
     mods = [ConvTranspose2d(128, 128).to(dev), GDN(128, inverse=True).to(dev)]; x = torch.randn(B, 128, 128, 192, device=dev); macs = B * 128 * 192 * 128 * 128 * 25 + B * 256 * 384 * 128 * 128
 with torch.no_grad():
-    xp = to_planes(x)
+    xp = to_planes(x) if kind != 'conv1' else x
     for _ in range(3): y = run_stack(mods + [Conv2d(128, 128, 3, 1).to(dev)][:0], xp) if False else None
     from compressai_environment_b200 import transforms as T
     def go():
-        if kind == "conv": return T._run_conv(mods[0], xp, None, ("planes",), None, gdn=(T._prep_gdn(mods[1]).packed, T._prep_gdn(mods[1]).bias, 1))
+        if kind in ("conv", "conv1"): return T._run_conv(mods[0], xp, None, ("planes",), None, gdn=(T._prep_gdn(mods[1]).packed, T._prep_gdn(mods[1]).bias, 1))
         return T._run_deconv(mods[0], xp, None, ("planes",), None, gdn=(T._prep_gdn(mods[1]).packed, T._prep_gdn(mods[1]).bias, 2))
     for _ in range(3): go()
     torch.cuda.synchronize()
