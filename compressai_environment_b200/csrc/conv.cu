@@ -43,6 +43,8 @@ constexpr int kMaxTaps = 32;
 constexpr uint32_t kLboA = kBM * 16u + 32u;
 constexpr uint32_t kSpinLimit = 1u << 28;
 
+__device__ long long g_conv_trace[64 * 8];  // experiment: phase timestamps of the first 64 CTAs (debug bit 32)
+
 struct ConvKernelParams {
   const __nv_bfloat16 *a_hi, *a_lo;  // [N, H, W, Cin] bf16 planes
   const unsigned char *w_packed;     // [n_tiles][ksteps][hi | lo] each BN x kBK bf16, canonical layout
@@ -138,6 +140,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -165,6 +190,8 @@ __device__ __forceinline__ Pack8 split8(const float *v) {
   return p;
 }
 
+#define CAI_TRACE(slot) do { if ((p.debug & 32) && blockIdx.x < 64 && blockIdx.y == 0 && tid == 0) g_conv_trace[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[4];
@@ -172,10 +199,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ __align__(8) uint64_t acc2_bar;
   __shared__ uint32_t s_tmem_base;
+  __shared__ int64_t s_opix[kBM];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN;
+  CAI_TRACE(0);
   const int stages = p.stages;
   const uint32_t a_plane = (kBK / 8) * kLboA;      // one bf16 plane of the A tile: kBK/8 chunks of kLboA bytes
   const uint32_t b_plane = static_cast<uint32_t>(BN) * kBK * 2;
@@ -211,6 +240,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  CAI_TRACE(1);
 
   if (warp < 4) {
     // ===================== producers =====================
@@ -325,8 +355,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     }
 
     // ===================== epilogue: thread = TMEM lane = pixel row =====================
+    CAI_TRACE(2);
     mbar_wait_bounded(&acc_bar, 0);
     tc_fence_after();
+    CAI_TRACE(3);
     const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
     if (fuse_gdn) {
       // ---- fused GDN, part 1: turn the accumulator into the A operand of the second GEMM.
@@ -344,18 +376,30 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           mbar_expect_tx(&full_bar[s], 2 * b_plane);
           tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
         }
-#pragma unroll 1
+        static_assert(kBK == 32, "the GDN operand phase loads one 32-column TMEM slab per k-step");
+        uint32_t raw[32];
+        const int col0 = g * kBK;
+        const bool any = col0 < BN;  // warp-uniform (BN is a multiple of 16: a k-step may be half empty)
+        if (any) {
+          tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0), raw);
+          tmem_wait_ld();
+        }
+#pragma unroll
         for (int c = 0; c < kBK / 8; ++c) {
-          const int col = g * kBK + c * 8;
+          const int col = col0 + c * 8;
           uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
-          if (col < BN) {  // warp-uniform
-            uint32_t raw[8];
-            tmem_ld8(tmem_base + lane_base + static_cast<uint32_t>(col), raw);
+          if (any && col < BN) {
             float sq[8];
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + col) + 1);
+              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+              bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float a = __uint_as_float(raw[i]);
-              if (p.bias) a += __ldg(p.bias + n0 + col + i);
+              const float a = __uint_as_float(raw[c * 8 + i]) + bb[i];
               sq[i] = a * a;
             }
             const Pack8 pk = split8(sq);
@@ -370,99 +414,194 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         asm volatile("bar.sync 1, 128;" ::: "memory");  // all four epilogue warps have written (and fenced) their rows
         if (is_loader) mbar_arrive(&full_bar[s]);     // same arrival count as a main-loop k-step
       }
+      CAI_TRACE(4);
       mbar_wait_bounded(&acc2_bar, 0);
       tc_fence_after();
+      CAI_TRACE(5);
     }
-    int64_t opix = 0;
+    // ---- output epilogue.  Each thread owns one pixel row of the accumulator; writing that row straight to
+    // global memory makes every warp store hit 32 different rows with 16-byte pieces (measured: ~38k cycles per
+    // tile).  Instead the tile is staged in the (now idle) operand ring with a padded row pitch and then copied
+    // out cooperatively, consecutive lanes covering consecutive 16-byte units of a row (full-line stores).
+    int64_t opix = -1;
     if (row_ok) {
       const int oy = pi * p.os + p.o0y, ox = pj * p.os + p.o0x;
       opix = (static_cast<int64_t>(n_img) * p.Ho + oy) * p.Wo + ox;
     }
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t raw[16];
-      tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
-      uint32_t raw2[16];
-      if (fuse_gdn) tmem_ld16(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
-      if (!row_ok || (p.debug & 8)) continue;
-      const int cg = n0 + c0;  // global output channel of raw[0]
-      if (cg >= p.Cout) continue;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(raw[i]);
-        if (p.bias && cg + i < p.Cout) a += __ldg(p.bias + cg + i);
-        v[i] = a;
+    s_opix[tid] = opix;
+    // staged buffers: fp32 tile and/or bf16 plane pairs (out, out^2, |out|)
+    struct StageBuf {
+      unsigned char *g;   // global base of the tensor (element (pixel 0, channel 0))
+      uint32_t off;       // byte offset of the staging buffer inside the ring
+      uint32_t esize;     // bytes per element
+    };
+    StageBuf bufs[7];
+    int nbuf = 0;
+    const int n_f32 = p.out_f32 ? 1 : 0;
+    const int n_pl = (p.out_hi ? 1 : 0) + (p.sq_hi ? 1 : 0) + (p.abs_hi ? 1 : 0);
+    const uint32_t ring_bytes = static_cast<uint32_t>(stages) * stage_bytes;
+    int ncols = BN;  // columns per pass: as many as fit the ring
+    while (ncols > 16 && kBM * (n_f32 * (ncols * 4u + 16u) + n_pl * 2u * (ncols * 2u + 16u)) > ring_bytes) ncols -= 16;
+    const uint32_t pitch_f = ncols * 4u + 16u, pitch_b = ncols * 2u + 16u;
+    {
+      uint32_t off = 0;
+      if (p.out_f32) {
+        bufs[nbuf++] = {reinterpret_cast<unsigned char *>(p.out_f32), off, 4u};
+        off += kBM * pitch_f;
       }
-      if (fuse_gdn) {
+      __nv_bfloat16 *pl[6] = {p.out_hi, p.out_lo, p.sq_hi, p.sq_lo, p.abs_hi, p.abs_lo};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float nrm = __uint_as_float(raw2[i]) + __ldg(p.gdn_beta + cg + i);
-          v[i] = (p.gdn_mode == 1) ? v[i] * rsqrtf(nrm) : v[i] * sqrtf(nrm);
+      for (int q = 0; q < 6; ++q) {
+        if (pl[q]) {
+          bufs[nbuf++] = {reinterpret_cast<unsigned char *>(pl[q]), off, 2u};
+          off += kBM * pitch_b;
         }
       }
-      const int64_t obase = opix * p.Cout + cg;
-      if (p.epilogue == 1) {
+    }
+    const uint32_t off_out = n_f32 * kBM * pitch_f;                   // first plane buffer
+    const uint32_t off_sq = off_out + (p.out_hi ? 2u : 0u) * kBM * pitch_b;
+    const uint32_t off_abs = off_sq + (p.sq_hi ? 2u : 0u) * kBM * pitch_b;
+
+    for (int cA = 0; cA < BN; cA += ncols) {
+      const int cB = (cA + ncols < BN) ? cA + ncols : BN;
+      // ---- phase 1: TMEM -> registers -> epilogue math -> staging (thread = row)
+      for (int c0 = cA; c0 < cB; c0 += 16) {
+        uint32_t raw[16];
+        uint32_t raw2[16];
+        tmem_ld16_nowait(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
+        if (fuse_gdn) tmem_ld16_nowait(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
+        tmem_wait_ld();
+        if (!row_ok || (p.debug & 8)) continue;
+        const int cg = n0 + c0;  // global output channel of raw[0]
+        if (cg >= p.Cout) continue;
+        float v[16];
+        if (p.bias) {
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cg);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      } else if (p.epilogue == 2) {
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = __ldg(b4 + q);
+            v[4 * q] = __uint_as_float(raw[4 * q]) + bb.x;
+            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bb.y;
+            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bb.z;
+            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bb.w;
+          }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
-      } else if (p.epilogue >= 3) {
-        const uint4 *ah = reinterpret_cast<const uint4 *>(p.aux_hi + obase);
-        const uint4 *al = reinterpret_cast<const uint4 *>(p.aux_lo + obase);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+        }
+        if (fuse_gdn) {
+          const float4 *g4 = reinterpret_cast<const float4 *>(p.gdn_beta + cg);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 qh = __ldg(ah + h), ql = __ldg(al + h);
-          const __nv_bfloat16 *bh = reinterpret_cast<const __nv_bfloat16 *>(&qh);
-          const __nv_bfloat16 *bl = reinterpret_cast<const __nv_bfloat16 *>(&ql);
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = __ldg(g4 + q);
+            const float be[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = __bfloat162float(bh[i]) + __bfloat162float(bl[i]);
-            const float nrm = v[h * 8 + i];
-            v[h * 8 + i] = (p.epilogue == 3) ? x * rsqrtf(nrm) : x * sqrtf(nrm);
+            for (int i = 0; i < 4; ++i) {
+              const float nrm = __uint_as_float(raw2[4 * q + i]) + be[i];
+              v[4 * q + i] = (p.gdn_mode == 1) ? v[4 * q + i] * rsqrtf(nrm) : v[4 * q + i] * sqrtf(nrm);
+            }
+          }
+        }
+        if (p.epilogue == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (p.epilogue == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+        } else if (p.epilogue >= 3) {
+          const int64_t obase = opix * p.Cout + cg;
+          const uint4 *ah = reinterpret_cast<const uint4 *>(p.aux_hi + obase);
+          const uint4 *al = reinterpret_cast<const uint4 *>(p.aux_lo + obase);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 qh = __ldg(ah + h), ql = __ldg(al + h);
+            const __nv_bfloat16 *bh = reinterpret_cast<const __nv_bfloat16 *>(&qh);
+            const __nv_bfloat16 *bl = reinterpret_cast<const __nv_bfloat16 *>(&ql);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = __bfloat162float(bh[i]) + __bfloat162float(bl[i]);
+              const float nrm = v[h * 8 + i];
+              v[h * 8 + i] = (p.epilogue == 3) ? x * rsqrtf(nrm) : x * sqrtf(nrm);
+            }
+          }
+        }
+        if (p.clamp_lo < p.clamp_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], p.clamp_lo), p.clamp_hi);
+        }
+        const uint32_t cc = static_cast<uint32_t>(c0 - cA);
+        if (p.out_f32) {
+          float4 *o = reinterpret_cast<float4 *>(smem + static_cast<uint32_t>(r) * pitch_f + cc * 4u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        const uint32_t rb = static_cast<uint32_t>(r) * pitch_b + cc * 2u;
+        if (p.out_hi) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const Pack8 pk = split8(v + 8 * h);
+            *reinterpret_cast<uint4 *>(smem + off_out + rb + h * 16u) = pk.hi;
+            *reinterpret_cast<uint4 *>(smem + off_out + kBM * pitch_b + rb + h * 16u) = pk.lo;
+          }
+        }
+        if (p.sq_hi) {
+          float sv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[i] = v[i] * v[i];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const Pack8 pk = split8(sv + 8 * h);
+            *reinterpret_cast<uint4 *>(smem + off_sq + rb + h * 16u) = pk.hi;
+            *reinterpret_cast<uint4 *>(smem + off_sq + kBM * pitch_b + rb + h * 16u) = pk.lo;
+          }
+        }
+        if (p.abs_hi) {
+          float sv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[i] = fabsf(v[i]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const Pack8 pk = split8(sv + 8 * h);
+            *reinterpret_cast<uint4 *>(smem + off_abs + rb + h * 16u) = pk.hi;
+            *reinterpret_cast<uint4 *>(smem + off_abs + kBM * pitch_b + rb + h * 16u) = pk.lo;
           }
         }
       }
-      if (p.clamp_lo < p.clamp_hi) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], p.clamp_lo), p.clamp_hi);
-      }
-      // Cout is a multiple of 16 for every tensor-core layer (host pads otherwise), so 16-wide stores are aligned
-      if (p.out_f32) {
-        float4 *o = reinterpret_cast<float4 *>(p.out_f32 + obase);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (p.out_hi) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const Pack8 pk = split8(v + 8 * h);
-          reinterpret_cast<uint4 *>(p.out_hi + obase)[h] = pk.hi;
-          reinterpret_cast<uint4 *>(p.out_lo + obase)[h] = pk.lo;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- phase 2: cooperative copy-out, 16-byte units, consecutive lanes along a row
+      const int cols_here = (cB - cA < p.Cout - (n0 + cA)) ? (cB - cA) : (p.Cout - (n0 + cA));
+      if (cols_here > 0 && !(p.debug & 8)) {
+#pragma unroll 1
+        for (int bi = 0; bi < nbuf; ++bi) {
+          const StageBuf sb = bufs[bi];
+          const uint32_t pitch = (sb.esize == 4u) ? pitch_f : pitch_b;
+          const uint32_t units = static_cast<uint32_t>(cols_here) * sb.esize / 16u;  // per row
+          unsigned char *gbase = sb.g + static_cast<int64_t>(n0 + cA) * sb.esize;
+          const int64_t row_stride = static_cast<int64_t>(p.Cout) * sb.esize;
+          if ((units & (units - 1u)) == 0u && units <= 128u) {
+            // power-of-two units per row (the common case): shift / mask indexing, rows_per_iter rows per sweep
+            const uint32_t j = tid & (units - 1u);
+            const uint32_t rows_per_iter = 128u / units;
+            uint32_t row = tid / units;  // tid >> log2(units); done once
+            const unsigned char *sp = smem + sb.off + row * pitch + j * 16u;
+            const uint32_t sp_step = rows_per_iter * pitch;
+            for (; row < kBM; row += rows_per_iter, sp += sp_step) {
+              const int64_t op = s_opix[row];
+              if (op >= 0) *reinterpret_cast<uint4 *>(gbase + op * row_stride + j * 16u) = *reinterpret_cast<const uint4 *>(sp);
+            }
+          } else {
+            const uint32_t total_u = kBM * units;
+            for (uint32_t u = tid; u < total_u; u += 128u) {
+              const uint32_t row = u / units, j = u - row * units;
+              const int64_t op = s_opix[row];
+              if (op < 0) continue;
+              const uint4 val = *reinterpret_cast<const uint4 *>(smem + sb.off + row * pitch + j * 16u);
+              *reinterpret_cast<uint4 *>(gbase + op * row_stride + j * 16u) = val;
+            }
+          }
         }
       }
-      if (p.sq_hi) {
-        float s[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s[i] = v[i] * v[i];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const Pack8 pk = split8(s + 8 * h);
-          reinterpret_cast<uint4 *>(p.sq_hi + obase)[h] = pk.hi;
-          reinterpret_cast<uint4 *>(p.sq_lo + obase)[h] = pk.lo;
-        }
-      }
-      if (p.abs_hi) {
-        float s[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s[i] = fabsf(v[i]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const Pack8 pk = split8(s + 8 * h);
-          reinterpret_cast<uint4 *>(p.abs_hi + obase)[h] = pk.hi;
-          reinterpret_cast<uint4 *>(p.abs_lo + obase)[h] = pk.lo;
-        }
-      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
   } else {
     // ===================== MMA issuer (warp 4, one elected lane) =====================
@@ -504,8 +643,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     }
   }
 
+  CAI_TRACE(6);
   tc_fence_before();
   __syncthreads();
+  CAI_TRACE(7);
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -702,6 +843,11 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   conv_gemm_kernel<<<dim3(static_cast<unsigned>(mt), static_cast<unsigned>(nt)), kConvThreads, smem,
                      static_cast<cudaStream_t>(stream_)>>>(p);
   CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+__attribute__((visibility("default"))) int cai_debug_conv_trace(long long *out_host) {  // experiment helper (not part of the documented ABI surface)
+  CAI_CUDA(cudaMemcpyFromSymbol(out_host, g_conv_trace, sizeof(long long) * 64 * 8));
   return CAI_OK;
 }
 

@@ -27,3 +27,14 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
 print(f"{kind} B={B}: {ms:.3f} ms  {2*macs/ms/1e9:.1f} TFLOP/s (algorithmic fp32-equivalent)")
+
+if os.environ.get("CAI_CONV_DEBUG") and int(os.environ["CAI_CONV_DEBUG"]) & 32:
+    import ctypes, numpy as np
+    from compressai_environment_b200._lib import lib
+    L = lib(); buf = (ctypes.c_longlong * 512)()
+    L._handle  # noqa
+    f = ctypes.CDLL(L._name).cai_debug_conv_trace; f.argtypes = [ctypes.c_void_p]; f(buf)
+    a = np.array(buf[:]).reshape(64, 8)
+    d = np.diff(a, axis=1)
+    print("phase cycles (median over 64 CTAs): prologue, producer-loop, wait-acc, gdnA, wait-acc2, epilogueB, final-sync")
+    print(np.median(d, axis=0).astype(int).tolist(), "total", int(np.median(a[:, 7] - a[:, 0])))
