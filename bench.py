@@ -319,6 +319,11 @@ def ours(args, rank, world):
     hbm = peaks.get("hbm_gbs", 6650.0)
     tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
     conv_tf = conv_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step else None
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/README.md)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     achieved = alg_bytes / (dec_avg * 1e-3) / 1e9 if dec_avg else None
     cpu = {"value": None}
     if not args.no_cpu_baseline:
@@ -341,7 +346,8 @@ def ours(args, rank, world):
         "gpu_launches": launches,
         "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv / deconv / fused GDN)", "bound": "tensor",
                      "achieved": conv_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (conv_tf / tpeak) if conv_tf else None,
-                     "traffic": None, "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_conv_traffic.json)",
+                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else
                                                       "fallback 1.4 PFLOP/s sustained"),
                      "alg_flops_per_launch": conv_flops_step / conv_launches_step if conv_launches_step else None,
                      "avg_launch_ms": conv_ms_step / conv_launches_step if conv_launches_step else None,
