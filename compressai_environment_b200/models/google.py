@@ -210,11 +210,15 @@ class ScaleHyperprior(CompressionModel):
     max_streams = 8
 
     def _streams(self, device, n):
+        """Internal streams are pooled PER CALLER STREAM: two requests issued on different user streams (e.g. two
+        host threads of a serving loop) get disjoint analysis / synthesis / coder streams, so one request waiting
+        for its decode never blocks the other's transforms (no head-of-line blocking on a shared in-order stream)."""
         pool = self.__dict__.setdefault("_stream_pool", {})
-        st = pool.get(str(device))
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        st = pool.get(key)
         if st is None:
             st = {"ana": torch.cuda.Stream(device=device), "syn": torch.cuda.Stream(device=device), "coder": []}
-            pool[str(device)] = st
+            pool[key] = st
         while len(st["coder"]) < n:
             st["coder"].append(torch.cuda.Stream(device=device, priority=-1))
         return st
