@@ -192,12 +192,18 @@ __device__ __forceinline__ Pack8 split8(const float *v) {
 
 #define CAI_TRACE(slot) do { if ((p.debug & 32) && blockIdx.x < 64 && blockIdx.y == 0 && tid == 0) g_conv_trace[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
+// KIND selects a specialised epilogue so that each instantiation stays small (the all-runtime-flags version is 33k
+// SASS instructions and thrashes the instruction cache in its epilogue loops):
+//   0 generic (every flag read at run time)        1 fused GDN / IGDN, split-plane output only
+//   2 linear / ReLU / LeakyReLU, plane output only  3 fp32 output (+ optional |.| planes), activation, clamp
+template <int KIND>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[4];
   __shared__ __align__(8) uint64_t empty_bar[4];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ __align__(8) uint64_t acc2_bar;
+  __shared__ __align__(8) uint64_t gfull_bar[8];  // GDN k-steps: each used once, 128 writer arrivals + gamma TMA
   __shared__ uint32_t s_tmem_base;
   __shared__ int64_t s_opix[kBM];
 
@@ -215,7 +221,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   const int n_tile = blockIdx.y;
   const int n0 = n_tile * BN;
 
-  const bool fuse_gdn = p.gdn_w != nullptr;
+  const bool fuse_gdn = (KIND == 0) ? (p.gdn_w != nullptr) : (KIND == 1);
+  const bool has_f32 = (KIND == 0) ? (p.out_f32 != nullptr) : (KIND == 3);
+  const bool has_out = (KIND == 0) ? (p.out_hi != nullptr) : (KIND == 1 || KIND == 2);
+  const bool has_sq = (KIND == 0) ? (p.sq_hi != nullptr) : false;
+  const bool has_abs = (KIND == 0 || KIND == 3) ? (p.abs_hi != nullptr) : false;
+  const int epi = (KIND == 1) ? 0 : p.epilogue;
+  const bool has_aux = (KIND == 0) ? (epi >= 3) : false;
+  const bool do_clamp = (KIND == 0 || KIND == 3) ? (p.clamp_lo < p.clamp_hi) : false;
   const int gdn_ksteps = fuse_gdn ? (BN + kBK - 1) / kBK : 0;
   uint32_t acc_cols = 32;
   while (acc_cols < static_cast<uint32_t>(BN)) acc_cols <<= 1;
@@ -228,6 +241,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     }
     mbar_init(&acc_bar, 1);
     mbar_init(&acc2_bar, 1);
+    for (int g = 0; g < 8; ++g) mbar_init(&gfull_bar[g], 128 + 1);
     mbar_fence_init();
   }
   if (warp == 4) {
@@ -252,14 +266,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     const int64_t m = m0 + r;
     const bool row_ok = m < M_total;
     int n_img = 0, pi = 0, pj = 0;
-    {
-      const int64_t per = static_cast<int64_t>(p.Hp) * p.Wp;
-      if (row_ok) {
-        n_img = static_cast<int>(m / per);
-        const int rem = static_cast<int>(m - n_img * per);
-        pi = rem / p.Wp;
-        pj = rem - pi * p.Wp;
-      }
+    const uint32_t per_img = static_cast<uint32_t>(p.Hp) * static_cast<uint32_t>(p.Wp);  // host checks M_total < 2^31
+    if (row_ok) {
+      const uint32_t mu = static_cast<uint32_t>(m);
+      n_img = static_cast<int>(mu / per_img);
+      const uint32_t rem = mu - static_cast<uint32_t>(n_img) * per_img;
+      pi = static_cast<int>(rem / static_cast<uint32_t>(p.Wp));
+      pj = static_cast<int>(rem - static_cast<uint32_t>(pi) * static_cast<uint32_t>(p.Wp));
     }
     const uint32_t row_off = (static_cast<uint32_t>(r) >> 3) * 128u + (static_cast<uint32_t>(r) & 7u) * 16u;
     const unsigned char *wbase = p.w_packed + static_cast<size_t>(n_tile) * ksteps * (2 * b_plane);
@@ -276,12 +289,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       ld_so[it] = static_cast<uint32_t>(lc) * kLboA + (static_cast<uint32_t>(lr) >> 3) * 128u +
                   (static_cast<uint32_t>(lr) & 7u) * 16u;
       if (lm < M_total) {
-        const int64_t per = static_cast<int64_t>(p.Hp) * p.Wp;
-        const int ni = static_cast<int>(lm / per);
-        const int rem = static_cast<int>(lm - ni * per);
-        const int li = rem / p.Wp;
-        ld_iy[it] = li * p.is;
-        ld_ix[it] = (rem - li * p.Wp) * p.is;
+        const uint32_t lmu = static_cast<uint32_t>(lm);
+        const uint32_t ni = lmu / per_img;
+        const uint32_t rem = lmu - ni * per_img;
+        const uint32_t li = rem / static_cast<uint32_t>(p.Wp);
+        ld_iy[it] = static_cast<int>(li) * p.is;
+        ld_ix[it] = static_cast<int>(rem - li * static_cast<uint32_t>(p.Wp)) * p.is;
         ld_img[it] = static_cast<int64_t>(ni) * p.H * p.W;
       } else {
         ld_iy[it] = -(1 << 28);
@@ -373,14 +386,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         }
         unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
         if (tid == 0) {
-          mbar_expect_tx(&full_bar[s], 2 * b_plane);
-          tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
+          mbar_expect_tx(&gfull_bar[g], 2 * b_plane);
+          tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &gfull_bar[g]);
         }
         static_assert(kBK == 32, "the GDN operand phase loads one 32-column TMEM slab per k-step");
         uint32_t raw[32];
         const int col0 = g * kBK;
         const bool any = col0 < BN;  // warp-uniform (BN is a multiple of 16: a k-step may be half empty)
-        if (any) {
+        if (any && !(p.debug & 128)) {
           tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0), raw);
           tmem_wait_ld();
         }
@@ -410,9 +423,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           *reinterpret_cast<uint4 *>(sa + so) = vh;
           *reinterpret_cast<uint4 *>(sa + a_plane + so) = vl;
         }
-        fence_async_proxy();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // all four epilogue warps have written (and fenced) their rows
-        if (is_loader) mbar_arrive(&full_bar[s]);     // same arrival count as a main-loop k-step
+        if (!(p.debug & 64)) fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&gfull_bar[g]);   // every writer arrives: no CTA-wide barrier needed
       }
       CAI_TRACE(4);
       mbar_wait_bounded(&acc2_bar, 0);
@@ -437,30 +449,31 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     };
     StageBuf bufs[7];
     int nbuf = 0;
-    const int n_f32 = p.out_f32 ? 1 : 0;
-    const int n_pl = (p.out_hi ? 1 : 0) + (p.sq_hi ? 1 : 0) + (p.abs_hi ? 1 : 0);
+    const int n_f32 = has_f32 ? 1 : 0;
+    const int n_pl = (has_out ? 1 : 0) + (has_sq ? 1 : 0) + (has_abs ? 1 : 0);
     const uint32_t ring_bytes = static_cast<uint32_t>(stages) * stage_bytes;
     int ncols = BN;  // columns per pass: as many as fit the ring
     while (ncols > 16 && kBM * (n_f32 * (ncols * 4u + 16u) + n_pl * 2u * (ncols * 2u + 16u)) > ring_bytes) ncols -= 16;
     const uint32_t pitch_f = ncols * 4u + 16u, pitch_b = ncols * 2u + 16u;
     {
       uint32_t off = 0;
-      if (p.out_f32) {
+      if (has_f32) {
         bufs[nbuf++] = {reinterpret_cast<unsigned char *>(p.out_f32), off, 4u};
         off += kBM * pitch_f;
       }
       __nv_bfloat16 *pl[6] = {p.out_hi, p.out_lo, p.sq_hi, p.sq_lo, p.abs_hi, p.abs_lo};
+      const bool use[6] = {has_out, has_out, has_sq, has_sq, has_abs, has_abs};
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
-        if (pl[q]) {
+        if (use[q]) {
           bufs[nbuf++] = {reinterpret_cast<unsigned char *>(pl[q]), off, 2u};
           off += kBM * pitch_b;
         }
       }
     }
     const uint32_t off_out = n_f32 * kBM * pitch_f;                   // first plane buffer
-    const uint32_t off_sq = off_out + (p.out_hi ? 2u : 0u) * kBM * pitch_b;
-    const uint32_t off_abs = off_sq + (p.sq_hi ? 2u : 0u) * kBM * pitch_b;
+    const uint32_t off_sq = off_out + (has_out ? 2u : 0u) * kBM * pitch_b;
+    const uint32_t off_abs = off_sq + (has_sq ? 2u : 0u) * kBM * pitch_b;
 
     for (int cA = 0; cA < BN; cA += ncols) {
       const int cB = (cA + ncols < BN) ? cA + ncols : BN;
@@ -498,17 +511,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float nrm = __uint_as_float(raw2[4 * q + i]) + be[i];
-              v[4 * q + i] = (p.gdn_mode == 1) ? v[4 * q + i] * rsqrtf(nrm) : v[4 * q + i] * sqrtf(nrm);
+              const float rs = rsqrtf(nrm);
+              v[4 * q + i] *= (p.gdn_mode == 1) ? rs : nrm * rs;  // n^-1/2 or n^+1/2 = n * n^-1/2
             }
           }
         }
-        if (p.epilogue == 1) {
+        if (epi == 1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else if (p.epilogue == 2) {
+        } else if (epi == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
-        } else if (p.epilogue >= 3) {
+        } else if (has_aux) {
           const int64_t obase = opix * p.Cout + cg;
           const uint4 *ah = reinterpret_cast<const uint4 *>(p.aux_hi + obase);
           const uint4 *al = reinterpret_cast<const uint4 *>(p.aux_lo + obase);
@@ -521,22 +535,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             for (int i = 0; i < 8; ++i) {
               const float x = __bfloat162float(bh[i]) + __bfloat162float(bl[i]);
               const float nrm = v[h * 8 + i];
-              v[h * 8 + i] = (p.epilogue == 3) ? x * rsqrtf(nrm) : x * sqrtf(nrm);
+              const float rs = rsqrtf(nrm);
+              v[h * 8 + i] = x * ((epi == 3) ? rs : nrm * rs);
             }
           }
         }
-        if (p.clamp_lo < p.clamp_hi) {
+        if (do_clamp) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], p.clamp_lo), p.clamp_hi);
         }
         const uint32_t cc = static_cast<uint32_t>(c0 - cA);
-        if (p.out_f32) {
+        if (has_f32) {
           float4 *o = reinterpret_cast<float4 *>(smem + static_cast<uint32_t>(r) * pitch_f + cc * 4u);
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         const uint32_t rb = static_cast<uint32_t>(r) * pitch_b + cc * 2u;
-        if (p.out_hi) {
+        if (has_out) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const Pack8 pk = split8(v + 8 * h);
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             *reinterpret_cast<uint4 *>(smem + off_out + kBM * pitch_b + rb + h * 16u) = pk.lo;
           }
         }
-        if (p.sq_hi) {
+        if (has_sq) {
           float sv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) sv[i] = v[i] * v[i];
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             *reinterpret_cast<uint4 *>(smem + off_sq + kBM * pitch_b + rb + h * 16u) = pk.lo;
           }
         }
-        if (p.abs_hi) {
+        if (has_abs) {
           float sv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) sv[i] = fabsf(v[i]);
@@ -568,6 +583,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cA == 0) CAI_TRACE(6);
       // ---- phase 2: cooperative copy-out, 16-byte units, consecutive lanes along a row
       const int cols_here = (cB - cA < p.Cout - (n0 + cA)) ? (cB - cA) : (p.Cout - (n0 + cA));
       if (cols_here > 0 && !(p.debug & 8)) {
@@ -612,7 +628,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     int s = 0;
     uint32_t mphase = 0;
     for (int ks = 0; ks < ksteps + gdn_ksteps; ++ks) {
-      mbar_wait_bounded(&full_bar[s], mphase);
+      if (ks < ksteps) mbar_wait_bounded(&full_bar[s], mphase);
+      else mbar_wait_bounded(&gfull_bar[ks - ksteps], 0);
       tc_fence_after();
       if (lane == 0) {
         const bool second = ks >= ksteps;  // GDN GEMM: A = x^2 planes written by the epilogue warps, B = gamma
@@ -643,10 +660,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     }
   }
 
-  CAI_TRACE(6);
+  CAI_TRACE(7);
   tc_fence_before();
   __syncthreads();
-  CAI_TRACE(7);
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -839,9 +855,30 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   const int64_t mt = (M_total + kBM - 1) / kBM;
   const int nt = (d->Cout + d->BN - 1) / d->BN;
   CAI_CHECK_ARG(mt <= 0x7fffffff && nt <= 65535, "cai_conv_gemm: grid too large");
-  CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  conv_gemm_kernel<<<dim3(static_cast<unsigned>(mt), static_cast<unsigned>(nt)), kConvThreads, smem,
-                     static_cast<cudaStream_t>(stream_)>>>(p);
+  CAI_CHECK_ARG(M_total < (1ll << 31), "cai_conv_gemm: more than 2^31 output pixels per launch");
+  // pick the specialised epilogue
+  int kind = 0;
+  const bool only_planes = d->out_hi && !d->out_f32 && !d->sq_hi && !d->abs_hi;
+  const bool no_clamp = !(d->clamp_lo < d->clamp_hi);
+  if (p.gdn_w && only_planes && no_clamp) kind = 1;
+  else if (!p.gdn_w && d->epilogue <= 2 && only_planes && no_clamp) kind = 2;
+  else if (!p.gdn_w && d->epilogue <= 2 && d->out_f32 && !d->out_hi && !d->sq_hi) kind = 3;
+  if (getenv("CAI_CONV_GENERIC")) kind = 0;
+  const dim3 grid(static_cast<unsigned>(mt), static_cast<unsigned>(nt));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+#define CAI_LAUNCH_KIND(K)                                                                                           \
+  do {                                                                                                               \
+    CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                  static_cast<int>(smem)));                                                          \
+    conv_gemm_kernel<K><<<grid, kConvThreads, smem, st>>>(p);                                                       \
+  } while (0)
+  switch (kind) {
+    case 1: CAI_LAUNCH_KIND(1); break;
+    case 2: CAI_LAUNCH_KIND(2); break;
+    case 3: CAI_LAUNCH_KIND(3); break;
+    default: CAI_LAUNCH_KIND(0); break;
+  }
+#undef CAI_LAUNCH_KIND
   CAI_LAUNCH_CHECK();
   return CAI_OK;
 }

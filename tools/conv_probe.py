@@ -36,5 +36,5 @@ if os.environ.get("CAI_CONV_DEBUG") and int(os.environ["CAI_CONV_DEBUG"]) & 32:
     f = ctypes.CDLL(L._name).cai_debug_conv_trace; f.argtypes = [ctypes.c_void_p]; f(buf)
     a = np.array(buf[:]).reshape(64, 8)
     d = np.diff(a, axis=1)
-    print("phase cycles (median over 64 CTAs): prologue, producer-loop, wait-acc, gdnA, wait-acc2, epilogueB, final-sync")
+    print("phase cycles (median over 64 CTAs): prologue, producer-loop, wait-acc, gdnA, wait-acc2, epiB-phase1(TMEM+math+STS), epiB-phase2(copy-out)")
     print(np.median(d, axis=0).astype(int).tolist(), "total", int(np.median(a[:, 7] - a[:, 0])))
