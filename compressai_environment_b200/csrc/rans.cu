@@ -23,6 +23,7 @@
 //   ((x/f) << 16) + x%f + start = x + start + q * (2^16 - f).
 // freq == 1 uses m = 2^64-1, shift 0 (q = x - 1) and folds the missing 2^16 - 1 into the bias.
 // The 65536-entry table of m lives in HBM/L2 and is gathered one chunk ahead of the chain.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -564,7 +565,7 @@ static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
   // SMs -- each CTA pins a copy of the table in shared memory -- and leave the rest of the chip to the
   // transform kernels running concurrently on other streams.
   int w = (B + dp.sm_count / 4 - 1) / (dp.sm_count / 4 > 0 ? dp.sm_count / 4 : 1);
-  if (w < 8) w = 8;
+  if (const char *ov = getenv("CAI_CODER_WARPS")) { const int v = atoi(ov); if (v >= 1 && v <= kMaxWarpsPerCta) w = w > v ? w : v; } else if (w < 8) w = 8;
   if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
   if (w > B) w = B < 1 ? 1 : B;
   int g = (B + w - 1) / w;

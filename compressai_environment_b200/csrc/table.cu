@@ -13,6 +13,7 @@
 // * LUT entry for (row, bucket b = cf >> shift): {start | freq << 16, s0}.  s0 is the symbol that
 //   contains the first cumulative frequency of the bucket; freq != 0 means the whole bucket lies
 //   inside symbol s0 (decode needs no search), freq == 0 means "search forward from s0".
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -197,6 +198,7 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
   // Shared memory budget: leave 40 KB for per-warp staging buffers (32 warps) and static smem.
   const int64_t budget = static_cast<int64_t>(dp.max_smem_optin) - 40 * 1024;
   int nb = 256;
+  if (const char *ov = getenv("CAI_LUT_BUCKETS")) { const int v = atoi(ov); if (v >= 1 && v <= 256 && (v & (v - 1)) == 0) nb = v; }
   while (nb > 1 && static_cast<int64_t>(base) + static_cast<int64_t>(K) * nb * 8 > budget) nb >>= 1;
   const int in_smem = static_cast<int64_t>(base) + static_cast<int64_t>(K) * nb * 8 <= budget;
   if (!in_smem) nb = 256;  // tables live in L2; keep the LUT fine

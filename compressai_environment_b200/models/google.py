@@ -209,19 +209,30 @@ class ScaleHyperprior(CompressionModel):
     # because nothing here synchronises the host, the analysis of the NEXT call overlaps this call's decode wait.
     max_streams = 8
 
+    coder_stream_pool = 24
+
     def _streams(self, device, n):
-        """Internal streams are pooled PER CALLER STREAM: two requests issued on different user streams (e.g. two
-        host threads of a serving loop) get disjoint analysis / synthesis / coder streams, so one request waiting
-        for its decode never blocks the other's transforms (no head-of-line blocking on a shared in-order stream)."""
+        """Shared, in-order transform streams -- "ana" (analysis), "hyp" (hyper-synthesis + index kernels: short work
+        that only ever waits for a z decode) and "syn" (g_s: waits for the long y decodes) -- so that the tensor-core
+        work of all in-flight requests executes in a deterministic FIFO order and a request waiting for its decode
+        never blocks another request's hyper-synthesis.  Coder streams come round-robin from a pool larger than the
+        number of chunks in flight, so two requests rarely queue on the same coder stream."""
         pool = self.__dict__.setdefault("_stream_pool", {})
-        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
-        st = pool.get(key)
+        st = pool.get(str(device))
         if st is None:
-            st = {"ana": torch.cuda.Stream(device=device), "syn": torch.cuda.Stream(device=device), "coder": []}
-            pool[key] = st
-        while len(st["coder"]) < n:
-            st["coder"].append(torch.cuda.Stream(device=device, priority=-1))
+            st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device),
+                  "syn": torch.cuda.Stream(device=device),
+                  "pool": [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.coder_stream_pool)],
+                  "next": 0}
+            pool[str(device)] = st
         return st
+
+    def _take_coder_streams(self, st, n):
+        out = []
+        for _ in range(n):
+            out.append(st["pool"][st["next"] % len(st["pool"])])
+            st["next"] += 1
+        return out
 
     @staticmethod
     def _handoff(stream, *tensors):
@@ -245,13 +256,14 @@ class ScaleHyperprior(CompressionModel):
         _lib.require_cuda(x, "inputs")
         eb_t, gc_t = self.entropy_bottleneck._table(), self.gaussian_conditional._table()
         starts = list(range(0, x.size(0), self.micro_batch))
-        S = self._streams(x.device, min(len(starts), self.max_streams))
+        S = self._streams(x.device, len(starts))
+        coder_streams = self._take_coder_streams(S, len(starts))
         ana = S["ana"]
         ana.wait_event(torch.cuda.current_stream(x.device).record_event())
         x.record_stream(ana)
         y_encs, z_encs, shape = [], [], None
         for k, i in enumerate(starts):
-            ck = S["coder"][k % len(S["coder"])]
+            ck = coder_streams[k]
             with torch.cuda.stream(ana):
                 y_sym, y_idx, z_sym, z_idx, shape = self._analysis_chunk(x[i:i + self.micro_batch])
                 self._handoff(ck, y_sym, y_idx, z_sym, z_idx)
@@ -277,9 +289,11 @@ class ScaleHyperprior(CompressionModel):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         eb_t, gc_t = eb._table(), gc._table()
         S = self._streams(device, 1)
-        syn = S["syn"]
+        syn, hyp = S["syn"], S["hyp"]
         main = torch.cuda.current_stream(device)
-        syn.wait_event(main.record_event())
+        ev_main = main.record_event()
+        syn.wait_event(ev_main)
+        hyp.wait_event(ev_main)
         C = eb._quantized_cdf.size(0)
         h, w = int(shape[0]), int(shape[1])
         # pass 1 (all chunks): z decode -> h_s -> indexes -> launch the y decode.  pass 2: dequantize + g_s.
@@ -292,12 +306,14 @@ class ScaleHyperprior(CompressionModel):
                 ck.wait_event(ready)
                 z_idx = kernels.channel_indexes(n, C, h * w, device)
                 z_sym = coder.decode(eb_t, z_words[0], z_idx, device_words=z_words[1], status_out=statuses)
-                self._handoff(syn, z_sym)
-            with torch.cuda.stream(syn):
+                self._handoff(hyp, z_sym)
+            with torch.cuda.stream(hyp):
                 z_hat = kernels.dequantize(z_sym, None, eb._get_medians(), (n, C, h, w), _CL)
                 scales_hat, means_hat = self._params(z_hat)
                 _, y_idx = kernels.gc_quantize_index(None, scales_hat, None, gc.scale_table, gc._bound_scale())
                 self._handoff(ck, y_idx)
+                if means_hat is not None:
+                    means_hat.record_stream(syn)
             with torch.cuda.stream(ck):
                 y_sym = coder.decode(gc_t, y_words[0], y_idx, device_words=y_words[1], status_out=statuses)
                 done = ck.record_event()  # "syn" must NOT wait here: that would serialise the chunks' decodes
@@ -305,6 +321,7 @@ class ScaleHyperprior(CompressionModel):
             pending.append((y_sym, means_hat, tuple(scales_hat.shape), done))
         outs = []
         with torch.cuda.stream(syn):
+            syn.wait_event(hyp.record_event())  # means_hat / shapes produced on "hyp"
             for y_sym, means_hat, shp, done in pending:
                 syn.wait_event(done)
                 y_hat = kernels.dequantize(y_sym, means_hat, None, shp, _CL)
@@ -325,11 +342,12 @@ class ScaleHyperprior(CompressionModel):
         _lib.require_cuda(self.gaussian_conditional._quantized_cdf, "model buffers")
         n = len(strings[0])
         starts = list(range(0, n, self.micro_batch))
-        S = self._streams(dev, min(max(len(starts), 1), self.max_streams))
+        S = self._streams(dev, len(starts))
+        coder_streams = self._take_coder_streams(S, len(starts))
         chunks = []
         for k, i in enumerate(starts):
             ys, zs = list(strings[0][i:i + self.micro_batch]), list(strings[1][i:i + self.micro_batch])
-            chunks.append((S["coder"][k % len(S["coder"])], (ys, None), (zs, None), len(ys)))
+            chunks.append((coder_streams[k], (ys, None), (zs, None), len(ys)))
         statuses = []
         out = self._decompress_chunks(chunks, shape, dev, statuses)
         torch.cuda.current_stream(dev).synchronize()  # one sync per call: surface decoder errors like the reference would
