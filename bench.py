@@ -320,6 +320,8 @@ def ours(args, rank, world):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
 
+        iso = isolated_kernels(net, mb, B, dev) if rank == 0 else None
+
     ms, e2e_ms = max_over_ranks([ms, e2e_s * 1e3], dev, world)
 
     if rank != 0:
@@ -369,6 +371,9 @@ def ours(args, rank, world):
                      "alg_flops_per_launch": conv_flops_step / conv_launches_step if conv_launches_step else None,
                      "avg_launch_ms": conv_ms_step / conv_launches_step if conv_launches_step else None,
                      "launches_per_step": conv_launches_step, "kernel_ms_per_step": conv_ms_step,
+                     "isolated": {"launch": iso["conv"]["launch"], "ms": iso["conv"]["ms"],
+                                  "achieved": iso["conv"]["tflops"], "frac": iso["conv"]["tflops"] / tpeak,
+                                  "how": "same kernel timed alone, L2 flushed, median of 5"} if iso else None,
                      "note": "algorithmic fp32-equivalent FLOPs; the kernel issues 3 bf16 MMAs per product "
                              "(split hi/lo operands), so tensor-pipe work is 3x the algorithmic figure"},
         "roofline_coder": {"kernel": "rans_decode_kernel (y strings)", "bound": "hbm", "achieved": achieved, "peak": hbm,
@@ -377,11 +382,59 @@ def ours(args, rank, world):
                      "avg_launch_ms": dec_avg, "alg_bytes_per_launch": alg_bytes,
                      "encode_avg_launch_ms": (sum(enc_ms[len(enc_ms) // 2:]) / max(1, len(enc_ms) - len(enc_ms) // 2))
                      if enc_ms else None},
+        "roofline_index": {"kernel": "gc_qi_nhwc_kernel (fused quantize + build_indexes, one step's y/scales)",
+                           "bound": "hbm", "achieved": iso["index"]["gbs"], "peak": hbm, "unit": "GB/s",
+                           "frac": iso["index"]["gbs"] / hbm, "traffic": None, "avg_launch_ms": iso["index"]["ms"],
+                           "alg_bytes_per_launch": iso["index"]["alg_bytes"],
+                           "how": "timed alone, L2 flushed, median of 5"} if iso else None,
         "cpu_baseline": cpu,
     }
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+def isolated_kernels(model, mb, B, dev):
+    """The two bounding kernels timed ALONE (no overlapping streams, L2 flushed between launches, CUDA events on the
+    launching stream): the largest conv_gemm launch of the path (g_a layer 2: 128->128 5x5 s2 + fused GDN on one
+    micro-batch) and the fused quantize+index kernel on one step's y / scales (channels-last, as the transforms
+    produce them)."""
+    import torch
+    from compressai_environment_b200 import transforms as T, _lib
+    from compressai_environment_b200.kernels import CAI_LAYOUT_NHWC
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    with torch.no_grad():
+        conv, gdn = model.g_a[2], model.g_a[3]
+        xp = T.to_planes(torch.randn(mb, N_CH, H // 2, W // 2, device=dev))
+        g = T._prep_gdn(gdn)
+        ms = timed(lambda: T._run_conv(conv, xp, None, ("planes",), None, gdn=(g.packed, g.bias, 1)))
+        macs = mb * (H // 4) * (W // 4) * (N_CH * N_CH * 25 + N_CH * N_CH)
+        out["conv"] = {"launch": "g_a[2]+GDN 128->128 5x5 s2, micro-batch %d" % mb, "ms": ms, "tflops": 2 * macs / ms / 1e9}
+        del xp
+        n = B * M_CH * (H // 16) * (W // 16)
+        y = torch.randn(B, H // 16, W // 16, M_CH, device=dev) * 5
+        sc = torch.rand(B, H // 16, W // 16, M_CH, device=dev) * 8 + 0.05
+        sym = torch.empty(n, dtype=torch.int32, device=dev); idx = torch.empty_like(sym)
+        tab = model.gaussian_conditional.scale_table.to(dev).float().contiguous()
+        L = _lib.lib()
+        ms = timed(lambda: _lib.check(L.cai_gc_quantize_index(
+            _lib.ptr(y), _lib.ptr(sc), None, _lib.ptr(tab), int(tab.numel()), 0.11, CAI_LAYOUT_NHWC, B, M_CH,
+            (H // 16) * (W // 16), _lib.ptr(sym), _lib.ptr(idx), _lib.current_stream()), "cai_gc_quantize_index"))
+        out["index"] = {"ms": ms, "gbs": 16 * n / ms / 1e6, "alg_bytes": 16 * n}
+    return out
 
 
 def main():

@@ -33,6 +33,7 @@
 namespace cai {
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
+constexpr int kMaxGdnK = 8;       // GDN k-steps per tile (BN <= 256)
 constexpr int kBK = 32;           // k elements per stage (2 x UMMA_K=16): small stages -> 2 CTAs per SM
 constexpr int kProducerThreads = 64;   // warps 0-1 issue the A-tile cp.async copies (fewer mbarrier arrivals per k-step)
 constexpr int kLoadIters = 8;          // rows per producer thread: kBM / (kProducerThreads / 4)
@@ -234,6 +235,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   while (acc_cols < static_cast<uint32_t>(BN)) acc_cols <<= 1;
   const uint32_t tmem_cols = fuse_gdn ? 2 * acc_cols : acc_cols;  // second accumulator at column acc_cols
 
+  __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_beta[256];
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], kProducerThreads + 1);
@@ -256,6 +259,16 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   const uint32_t tmem_base = s_tmem_base;
   CAI_TRACE(1);
 
+  if (warp == 2 || warp == 3) {
+    // bias / beta of this N tile -> shared memory (warps 2-3 idle through the main loop).  The epilogue reads them
+    // per column group, and a global load there -- L1 is being streamed through by the operand copies -- put an L2
+    // round trip on every group (measured: ~40% of the epilogue).  Published by the bar.sync after the acc wait.
+    for (int i = tid - 64; i < BN; i += 64) {
+      const bool in = n0 + i < p.Cout;
+      s_bias[i] = (p.bias && in) ? __ldg(p.bias + n0 + i) : 0.f;
+      s_beta[i] = (fuse_gdn && in) ? __ldg(p.gdn_beta + n0 + i) : 1.f;
+    }
+  }
   if (warp < 4) {
     // ===================== producers =====================
     // Load mapping: 4 lanes share one pixel (its kBK = 32 channels = 64 contiguous bytes per plane), a warp
@@ -369,15 +382,38 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
 
     // ===================== epilogue: thread = TMEM lane = pixel row =====================
     CAI_TRACE(2);
+    // gamma prefetch: the ring stages the GDN GEMM will use free up in MMA order while the main loop drains, so
+    // thread 0 claims the first min(stages, gdn_ksteps) of them as they free and starts their TMA loads now --
+    // the copies land while the remaining threads are still waiting for the accumulator.
+    const int gdn_pre = fuse_gdn ? (gdn_ksteps < stages ? gdn_ksteps : stages) : 0;
+    if (tid == 0) {
+      int s = ps, pass = ppass;
+      for (int g = 0; g < gdn_pre; ++g) {
+        if (pass > 0) mbar_wait_bounded(&empty_bar[s], (pass - 1) & 1);
+        mbar_expect_tx(&gfull_bar[g], 2 * b_plane);
+        tma_bulk_g2s(smem + static_cast<uint32_t>(s) * stage_bytes + 2 * a_plane,
+                     p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &gfull_bar[g]);
+        if (++s == stages) {
+          s = 0;
+          ++pass;
+        }
+      }
+    }
     mbar_wait_bounded(&acc_bar, 0);
     tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_beta visible to all epilogue warps
     CAI_TRACE(3);
     const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
     if (fuse_gdn) {
       // ---- fused GDN, part 1: turn the accumulator into the A operand of the second GEMM.
       // x = acc + bias; x^2 is split into bf16 planes and written, kBK channels (one k-step) at a time, into the
       // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
-      for (int g = 0; g < gdn_ksteps; ++g) {
+      // The TMEM load of slab g+1 is in flight while slab g is processed (two register buffers).
+      uint32_t rawbuf[2][32];
+      if (!(p.debug & 128)) tmem_ld32_nowait(tmem_base + lane_base, rawbuf[0]);
+#pragma unroll
+      for (int g = 0; g < kMaxGdnK; ++g) {
+        if (g >= gdn_ksteps) break;
         const int s = ps;
         if (ppass > 0) mbar_wait_bounded(&empty_bar[s], (ppass - 1) & 1);
         if (++ps == stages) {
@@ -385,31 +421,26 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           ++ppass;
         }
         unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
-        if (tid == 0) {
+        if (tid == 0 && g >= gdn_pre) {
           mbar_expect_tx(&gfull_bar[g], 2 * b_plane);
           tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &gfull_bar[g]);
         }
         static_assert(kBK == 32, "the GDN operand phase loads one 32-column TMEM slab per k-step");
-        uint32_t raw[32];
+        uint32_t (&raw)[32] = rawbuf[g & 1];
         const int col0 = g * kBK;
         const bool any = col0 < BN;  // warp-uniform (BN is a multiple of 16: a k-step may be half empty)
-        if (any && !(p.debug & 128)) {
-          tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0), raw);
-          tmem_wait_ld();
-        }
+        tmem_wait_ld();
+        if (g + 1 < gdn_ksteps && col0 + kBK < BN && !(p.debug & 128))
+          tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0 + kBK), rawbuf[(g + 1) & 1]);
 #pragma unroll
         for (int c = 0; c < kBK / 8; ++c) {
           const int col = col0 + c * 8;
           uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
           if (any && col < BN) {
             float sq[8];
-            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + col) + 1);
-              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
-              bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-            }
+            const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + col);
+            const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + col + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float a = __uint_as_float(raw[c * 8 + i]) + bb[i];
@@ -478,21 +509,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     for (int cA = 0; cA < BN; cA += ncols) {
       const int cB = (cA + ncols < BN) ? cA + ncols : BN;
       // ---- phase 1: TMEM -> registers -> epilogue math -> staging (thread = row)
-      for (int c0 = cA; c0 < cB; c0 += 16) {
-        uint32_t raw[16];
-        uint32_t raw2[16];
+      // The TMEM loads of column group c0+16 are in flight while group c0 is processed (two register buffers).
+      auto issue = [&](int c0, uint32_t (&raw)[16], uint32_t (&raw2)[16]) {
         tmem_ld16_nowait(tmem_base + lane_base + static_cast<uint32_t>(c0), raw);
         if (fuse_gdn) tmem_ld16_nowait(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
-        tmem_wait_ld();
-        if (!row_ok || (p.debug & 8)) continue;
+      };
+      auto process = [&](int c0, const uint32_t (&raw)[16], const uint32_t (&raw2)[16]) {
+        if (!row_ok || (p.debug & 8)) return;
         const int cg = n0 + c0;  // global output channel of raw[0]
-        if (cg >= p.Cout) continue;
+        if (cg >= p.Cout) return;
         float v[16];
         if (p.bias) {
-          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cg);
+          const float4 *b4 = reinterpret_cast<const float4 *>(s_bias + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bb = __ldg(b4 + q);
+            const float4 bb = b4[q];
             v[4 * q] = __uint_as_float(raw[4 * q]) + bb.x;
             v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bb.y;
             v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bb.z;
@@ -503,10 +534,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
         }
         if (fuse_gdn) {
-          const float4 *g4 = reinterpret_cast<const float4 *>(p.gdn_beta + cg);
+          const float4 *g4 = reinterpret_cast<const float4 *>(s_beta + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bb = __ldg(g4 + q);
+            const float4 bb = g4[q];
             const float be[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -581,6 +612,20 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             *reinterpret_cast<uint4 *>(smem + off_abs + kBM * pitch_b + rb + h * 16u) = pk.lo;
           }
         }
+      };
+      {
+        uint32_t qa[16], qa2[16], qb[16], qb2[16];
+        issue(cA, qa, qa2);
+        for (int c0 = cA; c0 < cB; c0 += 32) {
+          tmem_wait_ld();
+          if (c0 + 16 < cB) issue(c0 + 16, qb, qb2);
+          process(c0, qa, qa2);
+          if (c0 + 16 < cB) {
+            tmem_wait_ld();
+            if (c0 + 32 < cB) issue(c0 + 32, qa, qa2);
+            process(c0 + 16, qb, qb2);
+          }
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (cA == 0) CAI_TRACE(6);
@@ -601,6 +646,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             uint32_t row = tid / units;  // tid >> log2(units); done once
             const unsigned char *sp = smem + sb.off + row * pitch + j * 16u;
             const uint32_t sp_step = rows_per_iter * pitch;
+#pragma unroll 4
             for (; row < kBM; row += rows_per_iter, sp += sp_step) {
               const int64_t op = s_opix[row];
               if (op >= 0) *reinterpret_cast<uint4 *>(gbase + op * row_stride + j * 16u) = *reinterpret_cast<const uint4 *>(sp);
@@ -693,9 +739,14 @@ split_planes_kernel(const float *__restrict__ x, int layout, int64_t N, int64_t 
 // im2col for tiny Cin (first layer, Cin = 3): [N, H, W, C] fp32 (any layout) -> split planes [N*Ho*Wo, Kpad]
 // with k = (ky * ks + kx) * C + c, zero padded to Kpad.
 // One thread = one output pixel x one group of 8 k-values -> one 16-byte store per plane (coalesced along k).
+// CT / KT > 0 fix the channel count and kernel size at compile time (the codecs' first layer is C = 3, k = 5:
+// every division below becomes a multiply); 0 = runtime values.
+template <int CT, int KT>
 __global__ void __launch_bounds__(256)
-im2col_split_kernel(const float *__restrict__ x, int layout, int N, int C, int H, int W, int Ho, int Wo, int ksz,
+im2col_split_kernel(const float *__restrict__ x, int layout, int N, int C_, int H, int W, int Ho, int Wo, int ksz_,
                     int stride, int pad, int Kpad, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+  const int C = CT > 0 ? CT : C_;
+  const int ksz = KT > 0 ? KT : ksz_;
   const int groups = Kpad >> 3;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * groups;
   const int64_t gs = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -907,10 +958,13 @@ int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32
   DeviceProps dp;
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
-  im2col_split_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8)), 256, 0,
-                        static_cast<cudaStream_t>(stream_)>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad,
-                                                              static_cast<__nv_bfloat16 *>(hi),
-                                                              static_cast<__nv_bfloat16 *>(lo));
+  const int grid = ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  __nv_bfloat16 *h = static_cast<__nv_bfloat16 *>(hi), *l = static_cast<__nv_bfloat16 *>(lo);
+  if (C == 3 && ksize == 5)
+    im2col_split_kernel<3, 5><<<grid, 256, 0, st>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad, h, l);
+  else
+    im2col_split_kernel<0, 0><<<grid, 256, 0, st>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad, h, l);
   CAI_LAUNCH_CHECK();
   return CAI_OK;
 }

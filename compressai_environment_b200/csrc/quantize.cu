@@ -94,38 +94,89 @@ gc_qi_nchw_kernel(const float *__restrict__ y, const float *__restrict__ scales,
   }
 }
 
-// ---- NHWC -> coder order (32x32 tile transpose) --------------------------------------------------------
-// grid: x = hw tiles, y = c tiles, z = n ; block (32, 8)
+// ---- NHWC -> coder order (tile transpose) -------------------------------------------------------------
+// Tile = 32 pixels (hw) x 64 channels.  Loads: float4 along the channel axis (16 threads cover the 256
+// contiguous bytes of one pixel's 64 channels; 256 threads = 16 pixels per pass, 2 passes).  Stores: int4 along
+// the hw axis (8 threads cover the 128 contiguous bytes of one channel's 32 pixels; 32 channels per pass, 2 passes).
+// Both directions move full 128-byte lines; the int32 tiles are transposed through padded shared memory.
+// grid: x = hw tiles, y = c tiles, z = n ; block 256
+constexpr int kTH = 32, kTC = 64;
+
 __global__ void __launch_bounds__(256)
 gc_qi_nhwc_kernel(const float *__restrict__ y, const float *__restrict__ scales, const float *__restrict__ means,
                   const float *__restrict__ table, int T, float bound, int64_t C, int64_t HW,
                   int32_t *__restrict__ sym, int32_t *__restrict__ idx) {
   extern __shared__ float s_tab[];
-  __shared__ int32_t t_sym[32][33];
-  __shared__ int32_t t_idx[32][33];
+  __shared__ int32_t t_sym[kTC][kTH + 1];
+  __shared__ int32_t t_idx[kTC][kTH + 1];
   const int rep = (T <= kMaxRepT) ? kTabRep : 1;
   if (scales) load_table(s_tab, table, T, rep);
-  ScaleTab st{s_tab, T, rep, static_cast<int>(threadIdx.x)};
+  ScaleTab st{s_tab, T, rep, static_cast<int>(threadIdx.x & 31)};
   const int64_t n = blockIdx.z;
-  const int64_t hw0 = static_cast<int64_t>(blockIdx.x) * 32, c0 = static_cast<int64_t>(blockIdx.y) * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t hw0 = static_cast<int64_t>(blockIdx.x) * kTH, c0 = static_cast<int64_t>(blockIdx.y) * kTC;
+  const int tid = threadIdx.x;
+  const bool vec_ok = (C & 3) == 0;  // float4 loads need C % 4 == 0 (bases are 16-byte aligned by the host check)
+  {
+    const int cq = tid & 15, hr = tid >> 4;  // 16 channel quads x 16 pixels per pass
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t hw = hw0 + ty + 8 * r, c = c0 + tx;
-    if (hw < HW && c < C) {
-      const int64_t i = (n * HW + hw) * C + c;
-      if (y) t_sym[ty + 8 * r][tx] = quant_sym(__ldcs(y + i), means ? __ldcs(means + i) : 0.f);
-      if (scales) t_idx[ty + 8 * r][tx] = st.index_of(__ldcs(scales + i), bound);
+    for (int pss = 0; pss < kTH / 16; ++pss) {
+      const int hl = hr + 16 * pss;
+      const int64_t hw = hw0 + hl, c = c0 + 4 * cq;
+      if (hw >= HW || c >= C) continue;
+      const int64_t base = (n * HW + hw) * C + c;
+      float yv[4] = {0.f, 0.f, 0.f, 0.f}, mv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec_ok && c + 3 < C) {
+        if (y) {
+          const float4 a = __ldcs(reinterpret_cast<const float4 *>(y + base));
+          yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w;
+          if (means) {
+            const float4 m = __ldcs(reinterpret_cast<const float4 *>(means + base));
+            mv[0] = m.x; mv[1] = m.y; mv[2] = m.z; mv[3] = m.w;
+          }
+        }
+        if (scales) {
+          const float4 q = __ldcs(reinterpret_cast<const float4 *>(scales + base));
+          sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (c + j < C) {
+            if (y) yv[j] = __ldcs(y + base + j);
+            if (y && means) mv[j] = __ldcs(means + base + j);
+            if (scales) sv[j] = __ldcs(scales + base + j);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (y) t_sym[4 * cq + j][hl] = quant_sym(yv[j], mv[j]);
+        if (scales) t_idx[4 * cq + j][hl] = st.index_of(sv[j], bound);
+      }
     }
   }
   __syncthreads();
+  {
+    const int hq = tid & 7, cr = tid >> 3;  // 8 pixel quads x 32 channels per pass
+    const bool out_vec = (HW & 3) == 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t c = c0 + ty + 8 * r, hw = hw0 + tx;
-    if (hw < HW && c < C) {
+    for (int pss = 0; pss < kTC / 32; ++pss) {
+      const int cl = cr + 32 * pss;
+      const int64_t c = c0 + cl, hw = hw0 + 4 * hq;
+      if (c >= C || hw >= HW) continue;
       const int64_t o = (n * C + c) * HW + hw;
-      if (y) sym[o] = t_sym[tx][ty + 8 * r];
-      if (scales) idx[o] = t_idx[tx][ty + 8 * r];
+      if (out_vec && hw + 3 < HW) {
+        if (y) *reinterpret_cast<int4 *>(sym + o) = make_int4(t_sym[cl][4 * hq], t_sym[cl][4 * hq + 1], t_sym[cl][4 * hq + 2], t_sym[cl][4 * hq + 3]);
+        if (scales) *reinterpret_cast<int4 *>(idx + o) = make_int4(t_idx[cl][4 * hq], t_idx[cl][4 * hq + 1], t_idx[cl][4 * hq + 2], t_idx[cl][4 * hq + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (hw + j < HW) {
+            if (y) sym[o + j] = t_sym[cl][4 * hq + j];
+            if (scales) idx[o + j] = t_idx[cl][4 * hq + j];
+          }
+        }
+      }
     }
   }
 }
@@ -246,10 +297,14 @@ int cai_gc_quantize_index(const float *y, const float *scales, const float *mean
     gc_qi_nchw_kernel<<<grid, 256, smem, stream>>>(y, scales, means, scale_table, T, scale_bound, total,
                                                    aligned ? 1 : 0, sym, idx);
   } else {
-    CAI_CHECK_ARG(N <= 65535 && (C + 31) / 32 <= 65535, "cai_gc_quantize_index: N or C too large for the grid");
-    dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(N));
-    gc_qi_nhwc_kernel<<<grid, dim3(32, 8), smem, stream>>>(y, scales, means, scale_table, T, scale_bound, C, HW, sym,
-                                                           idx);
+    CAI_CHECK_ARG(N <= 65535 && (C + kTC - 1) / kTC <= 65535, "cai_gc_quantize_index: N or C too large for the grid");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(scales) |
+                           reinterpret_cast<uintptr_t>(means) | reinterpret_cast<uintptr_t>(sym) |
+                           reinterpret_cast<uintptr_t>(idx)) & 15u) == 0;
+    CAI_CHECK_ARG(aligned, "cai_gc_quantize_index: NHWC tensors must be 16-byte aligned");
+    dim3 grid(static_cast<unsigned>((HW + kTH - 1) / kTH), static_cast<unsigned>((C + kTC - 1) / kTC),
+              static_cast<unsigned>(N));
+    gc_qi_nhwc_kernel<<<grid, 256, smem, stream>>>(y, scales, means, scale_table, T, scale_bound, C, HW, sym, idx);
   }
   CAI_LAUNCH_CHECK();
   return CAI_OK;

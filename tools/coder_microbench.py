@@ -40,6 +40,6 @@ sc = torch.exp(torch.rand((a.B, a.n), generator=gen, device=dev) * 8 - 3)
 ms, _ = timed(lambda: kernels.gc_quantize_index(y.view(a.B, a.n, 1), sc.view(a.B, a.n, 1), None, tab, 0.11), a.iters)
 print(f"gc_quantize_index nchw: {ms:.3f} ms  {16*nsym/ms/1e6:.1f} GB/s")
 if a.n % 192 == 0:
-    y4 = y.view(a.B, 192, -1, 1).contiguous(memory_format=torch.channels_last); s4 = sc.view(a.B, 192, -1, 1).contiguous(memory_format=torch.channels_last)
+    y4 = y.view(a.B, 192, -1, 1).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2); s4 = sc.view(a.B, 192, -1, 1).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
     ms, _ = timed(lambda: kernels.gc_quantize_index(y4, s4, None, tab, 0.11), a.iters)
     print(f"gc_quantize_index nhwc: {ms:.3f} ms  {16*nsym/ms/1e6:.1f} GB/s")
