@@ -780,6 +780,126 @@ im2col_split_kernel(const float *__restrict__ x, int layout, int N, int C_, int 
   }
 }
 
+// Tiled im2col for the codecs' first layer (C = 3, k = 5, s = 2, p = 2).  The block stages the fp32 input patch of a
+// 4 x 64 output tile (11 x 131 x 3 floats, read once with coalesced row segments) in shared memory and builds the
+// split-plane rows from there, so the 75 taps of a pixel cost shared-memory reads instead of 75 scattered global
+// loads; stores stay one 16-byte unit per (pixel, k-group), contiguous across the tile row.
+constexpr int kI2cTY = 4, kI2cTX = 64;
+constexpr int kI2cPR = 2 * kI2cTY + 3, kI2cPC = 2 * kI2cTX + 3, kI2cPitch = kI2cPC + 1;
+__global__ void __launch_bounds__(256)
+im2col_k5s2_c3_kernel(const float *__restrict__ x, int layout, int H, int W, int Ho, int Wo, int Kpad,
+                      __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+  __shared__ float s_patch[3][kI2cPR][kI2cPitch];
+  const int n = blockIdx.z, oy0 = blockIdx.y * kI2cTY, ox0 = blockIdx.x * kI2cTX;
+  const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+  for (int u = threadIdx.x; u < 3 * kI2cPR * kI2cPC; u += 256) {
+    const int c = u / (kI2cPR * kI2cPC), rem = u - c * (kI2cPR * kI2cPC);
+    const int r = rem / kI2cPC, col = rem - r * kI2cPC;
+    const int iy = iy0 + r, ix = ix0 + col;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = (layout == CAI_LAYOUT_NHWC) ? __ldg(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * 3 + c)
+                                      : __ldg(x + ((static_cast<int64_t>(n) * 3 + c) * H + iy) * W + ix);
+    s_patch[c][r][col] = v;
+  }
+  __syncthreads();
+  const int groups = Kpad >> 3;
+  for (int i = threadIdx.x; i < kI2cTY * kI2cTX * groups; i += 256) {
+    const int pix = i / groups, g = i - pix * groups;
+    const int py = pix / kI2cTX, px = pix - py * kI2cTX;
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy >= Ho || ox >= Wo) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 75) {
+        const int t = k / 3, c = k - 3 * t;
+        const int ky = t / 5, kx = t - 5 * ky;
+        val = s_patch[c][2 * py + ky][2 * px + kx];
+      }
+      v[j] = val;
+    }
+    const Pack8 pk = split8(v);
+    const int64_t o = ((static_cast<int64_t>(n) * Ho + oy) * Wo + ox) * Kpad + g * 8;
+    *reinterpret_cast<uint4 *>(hi + o) = pk.hi;
+    *reinterpret_cast<uint4 *>(lo + o) = pk.lo;
+  }
+}
+
+// Tiled col2im for the codecs' last layer (Cout = 3, k = 5, s = 2, p = 2, output_padding = 1 -> Ho = 2H, Wo = 2W).
+// The generic gather below reads each 320-byte cols row from ~25 different threads spread over the grid (measured:
+// 3.5x the algorithmic DRAM traffic).  Here a block stages the cols rows of the (4+2) x (32+2) input pixels that
+// feed an 8 x 64 output tile (float4 loads, whole rows) into shared memory with an odd pixel pitch, and each thread
+// produces two horizontally adjacent output pixels (even ox: kx = 0, 2, 4; odd ox: kx = 1, 3) for all three channels.
+constexpr int kC2iTY = 8, kC2iTX = 64;
+constexpr int kC2iIY = kC2iTY / 2 + 2, kC2iIX = kC2iTX / 2 + 2;
+constexpr int kC2iPitch = 77;  // words per staged pixel: 75 used, odd -> lanes on consecutive pixels hit distinct banks
+constexpr int kC2iSmem = kC2iIY * kC2iIX * kC2iPitch * 4;
+__global__ void __launch_bounds__(256)
+col2im_k5s2_c3_kernel(const float *__restrict__ cols, const float *__restrict__ bias, int H, int W, int Ho, int Wo,
+                      int Npad, int out_layout, float clamp_lo, float clamp_hi, float *__restrict__ out) {
+  extern __shared__ float s_cols[];
+  const int n = blockIdx.z, oy0 = blockIdx.y * kC2iTY, ox0 = blockIdx.x * kC2iTX;
+  const int iy0 = oy0 / 2 - 1, ix0 = ox0 / 2 - 1;
+  for (int u = threadIdx.x; u < kC2iIY * kC2iIX * 19; u += 256) {
+    const int pix = u / 19, q = u - pix * 19;
+    const int ly = pix / kC2iIX, lx = pix - ly * kC2iIX;
+    const int iy = iy0 + ly, ix = ix0 + lx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = __ldcs(reinterpret_cast<const float4 *>(cols + ((static_cast<int64_t>(n) * H + iy) * W + ix) * Npad) + q);
+    float *d = s_cols + pix * kC2iPitch + q * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 5, jx = threadIdx.x & 31;
+  const int oy = oy0 + ty, ox = ox0 + 2 * jx;
+  if (oy >= Ho || ox >= Wo) return;
+  float acc[2][3];
+#pragma unroll
+  for (int co = 0; co < 3; ++co) acc[0][co] = acc[1][co] = bias ? __ldg(bias + co) : 0.f;
+  for (int ky = ty & 1; ky < 5; ky += 2) {            // (oy + 2) % 2 == ty % 2 because oy0 is even
+    const int ly = (ty + 2 - ky) / 2 + 1;
+    const float *row = s_cols + (ly * kC2iIX + jx) * kC2iPitch + ky * 15;
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      acc[0][co] += row[2 * kC2iPitch + co];          // kx = 0 -> input pixel jx + 2
+      acc[0][co] += row[1 * kC2iPitch + 6 + co];      // kx = 2 -> jx + 1
+      acc[0][co] += row[12 + co];                     // kx = 4 -> jx
+      acc[1][co] += row[2 * kC2iPitch + 3 + co];      // kx = 1 -> jx + 2
+      acc[1][co] += row[1 * kC2iPitch + 9 + co];      // kx = 3 -> jx + 1
+    }
+  }
+  if (clamp_lo < clamp_hi) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) acc[e][co] = fminf(fmaxf(acc[e][co], clamp_lo), clamp_hi);
+  }
+  const bool two = ox + 1 < Wo;
+  if (out_layout == CAI_LAYOUT_NHWC) {
+    float *o = out + ((static_cast<int64_t>(n) * Ho + oy) * Wo + ox) * 3;
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      o[co] = acc[0][co];
+      if (two) o[3 + co] = acc[1][co];
+    }
+  } else {
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      float *o = out + ((static_cast<int64_t>(n) * 3 + co) * Ho + oy) * Wo + ox;
+      if (two && (Wo & 1) == 0) {
+        *reinterpret_cast<float2 *>(o) = make_float2(acc[0][co], acc[1][co]);
+      } else {
+        o[0] = acc[0][co];
+        if (two) o[1] = acc[1][co];
+      }
+    }
+  }
+}
+
 // col2im gather for tiny Cout (last deconv, Cout = 3): cols fp32 [N*H*W, Npad] with n = (ky*ks+kx)*Cout + co
 // -> out fp32 NCHW or NHWC [N, Cout, Ho, Wo], out(oy, ox) = bias + sum over taps with (oy + pad - ky) % stride == 0
 __global__ void __launch_bounds__(256)
@@ -961,7 +1081,10 @@ int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32
   const int grid = ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   __nv_bfloat16 *h = static_cast<__nv_bfloat16 *>(hi), *l = static_cast<__nv_bfloat16 *>(lo);
-  if (C == 3 && ksize == 5)
+  if (C == 3 && ksize == 5 && stride == 2 && pad == 2 && Kpad >= 75 && N <= 65535 && !getenv("CAI_PATCH_GENERIC")) {
+    dim3 tg((Wo + kI2cTX - 1) / kI2cTX, (Ho + kI2cTY - 1) / kI2cTY, N);
+    im2col_k5s2_c3_kernel<<<tg, 256, 0, st>>>(x, layout, H, W, Ho, Wo, Kpad, h, l);
+  } else if (C == 3 && ksize == 5)
     im2col_split_kernel<3, 5><<<grid, 256, 0, st>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad, h, l);
   else
     im2col_split_kernel<0, 0><<<grid, 256, 0, st>>>(x, layout, N, C, H, W, Ho, Wo, ksize, stride, pad, Kpad, h, l);
@@ -976,8 +1099,20 @@ int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, in
   DeviceProps dp;
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
-  col2im_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * Cout), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      cols, bias, N, Cout, H, W, Ho, Wo, ksize, stride, pad, Npad, out_layout, clamp_lo, clamp_hi, out);
+  if (Cout == 3 && ksize == 5 && stride == 2 && pad == 2 && Ho == 2 * H && Wo == 2 * W && Npad % 4 == 0 && Npad >= 76 &&
+      N <= 65535 && (reinterpret_cast<uintptr_t>(cols) & 15u) == 0 && !getenv("CAI_PATCH_GENERIC")) {
+    static bool attr_set = false;  // benign race: the attribute is idempotent
+    if (!attr_set) {
+      CAI_CUDA(cudaFuncSetAttribute(col2im_k5s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem));
+      attr_set = true;
+    }
+    dim3 tg((Wo + kC2iTX - 1) / kC2iTX, (Ho + kC2iTY - 1) / kC2iTY, N);
+    col2im_k5s2_c3_kernel<<<tg, 256, kC2iSmem, static_cast<cudaStream_t>(stream_)>>>(
+        cols, bias, H, W, Ho, Wo, Npad, out_layout, clamp_lo, clamp_hi, out);
+  } else {
+    col2im_kernel<<<ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * Cout), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        cols, bias, N, Cout, H, W, Ho, Wo, ksize, stride, pad, Npad, out_layout, clamp_lo, clamp_hi, out);
+  }
   CAI_LAUNCH_CHECK();
   return CAI_OK;
 }

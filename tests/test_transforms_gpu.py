@@ -53,6 +53,36 @@ def test_deconv(cin, cout, hw):
             _check(run_stack([m, torch.nn.ReLU()], x), F.relu(ref))
 
 
+@pytest.mark.parametrize("hw", [(67, 131), (5, 9), (64, 130), (33, 200)])
+def test_first_and_last_layer_tiled_patch_kernels(hw, monkeypatch):
+    """Cin = 3 / Cout = 3 layers go through the shared-memory tiled im2col / col2im kernels; ragged tile edges, both
+    input layouts, both output layouts, and agreement with the generic gather kernels (CAI_PATCH_GENERIC=1)."""
+    from compressai_environment_b200.transforms import Conv2d, ConvTranspose2d, run_stack
+
+    torch.manual_seed(3)
+    c1 = Conv2d(3, 32, 5, 2).to(DEV)
+    d1 = ConvTranspose2d(32, 3, 5, 2).to(DEV)
+    x = torch.rand(3, 3, *hw, device=DEV)
+    z = torch.randn(3, 32, *hw, device=DEV)
+    with torch.no_grad():
+        ref_c = F.conv2d(x, c1.weight, c1.bias, stride=2, padding=2)
+        ref_d = F.conv_transpose2d(z, d1.weight, d1.bias, stride=2, padding=2, output_padding=1)
+        got_c = run_stack([c1], x)
+        got_c_cl = run_stack([c1], x.contiguous(memory_format=torch.channels_last))
+        got_d = run_stack([d1], z)
+        got_d_clamp = run_stack([d1], z, clamp=(0.0, 1.0), nchw_out=True)
+        _check(got_c, ref_c)
+        _check(got_c_cl, ref_c)
+        _check(got_d, ref_d)
+        _check(got_d_clamp, ref_d.clamp(0, 1))
+        assert got_d_clamp.is_contiguous()
+        monkeypatch.setenv("CAI_PATCH_GENERIC", "1")
+        gen_c = run_stack([c1], x)
+        gen_d = run_stack([d1], z)
+        assert torch.equal(gen_c, got_c)          # same planes -> same GEMM -> identical
+        _check(gen_d, got_d, rtol=1e-6)           # same addends, different summation order
+
+
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("C", [128, 192, 32])
 def test_gdn(C, inverse):
