@@ -222,9 +222,21 @@ def ours(args, rank, world):
     out_hosts = [torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory() for _ in range(n_e2e_workers)]
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(n_e2e_workers)]
 
-    def step_e2e(slot=0):
+    import queue
+    free_slots = queue.SimpleQueue()
+    for i in range(n_e2e_workers):
+        free_slots.put(i)
+
+    def step_e2e(_=0):
         """One request through the PUBLIC API with host buffers: pinned images -> H2D -> model.compress() (bytes on
         the host) -> model.decompress(bytes) -> reconstruction copied to a caller-provided pinned buffer."""
+        slot = free_slots.get()   # one stream + one pinned output buffer per request in flight
+        try:
+            return _step_e2e(slot)
+        finally:
+            free_slots.put(slot)
+
+    def _step_e2e(slot):
         torch.cuda.set_device(local)
         with torch.cuda.stream(e2e_streams[slot]), torch.no_grad():
             xb = x_host.to(dev, non_blocking=True)
@@ -445,7 +457,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=32)
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -82,8 +82,21 @@ def slot_words(n: int) -> int:
     return int(lib().cai_rans_slot_words(int(n)))
 
 
+def to_host(t: torch.Tensor) -> torch.Tensor:
+    """Device -> host read that only blocks THIS thread.  ``tensor.cpu()`` copies into pageable memory: the driver
+    runs that copy synchronously and other host threads' CUDA calls queue behind it until the producing kernels have
+    finished (measured in the serving loop: every other request stalled for the length of an encode).  A pinned
+    destination + stream synchronise has no such side effect."""
+    if not t.is_cuda:
+        return t
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
+
+
 def _raise_status(status: torch.Tensor, what: str):
-    st = status.cpu()
+    st = to_host(status)
     bad = torch.nonzero(st != 0).reshape(-1)
     hard = [int(i) for i in bad if int(st[i]) != 6]
     if hard:
@@ -110,7 +123,7 @@ class EncodedBatch:
         if B == 0:
             return []
         dev = self.slots.device
-        nw = self.n_words.cpu()  # sync point: sizes are needed to allocate the packed buffer
+        nw = to_host(self.n_words)  # sync point: sizes are needed to allocate the packed buffer
         _raise_status(self.status, "rANS encode")
         total = int(nw.sum())
         begin = torch.empty(B + 1, dtype=torch.int64, device=dev)
@@ -128,6 +141,64 @@ class EncodedBatch:
             out.append(raw[a:e].tobytes())
             a = int(e)
         return out
+
+
+def batches_to_bytes(batches: Sequence[EncodedBatch]) -> List[List[bytes]]:
+    """``to_bytes()`` for several EncodedBatches with TWO host synchronisations in total instead of two per batch:
+    all sizes come back in one copy, every batch is compacted into its own range of one packed buffer, and one
+    device->host copy brings all strings back.  Batches may live on different streams (``batch.stream``)."""
+    batches = list(batches)
+    live = [b for b in batches if b.n_words.numel()]
+    if not live:
+        return [[] for _ in batches]
+    dev = live[0].slots.device
+    cur = torch.cuda.current_stream(dev)
+    for b in live:
+        st = getattr(b, "stream", None)
+        if st is not None and st != cur:
+            cur.wait_event(st.record_event())
+            for t in (b.slots, b.n_words, b.status):
+                t.record_stream(cur)
+    counts = [int(b.n_words.numel()) for b in live]
+    both = to_host(torch.cat([torch.cat([b.n_words for b in live]), torch.cat([b.status for b in live])]))  # sync 1
+    nw_all, st_all = both[:sum(counts)].numpy().astype(np.int64), both[sum(counts):]
+    if int(st_all.abs().max()) != 0:
+        for b in live:
+            _raise_status(b.status, "rANS encode")
+    totals, a = [], 0
+    for c in counts:
+        totals.append(int(nw_all[a:a + c].sum()))
+        a += c
+    grand = sum(totals)
+    packed = torch.empty(max(grand, 1), dtype=torch.int32, device=dev)
+    begin = torch.empty(sum(counts) + len(live), dtype=torch.int64, device=dev)
+    off = boff = 0
+    with torch.cuda.device(dev):
+        for b, c, tot in zip(live, counts, totals):
+            check(lib().cai_rans_compact(ptr(b.slots), b.slot_w, ptr(b.n_words), c, ptr(begin[boff:boff + c + 1]),
+                                         ptr(packed[off:]) if tot else ptr(packed), tot, current_stream()),
+                  "cai_rans_compact")
+            off += tot
+            boff += c + 1
+    host = torch.empty(max(grand, 1), dtype=torch.int32, pin_memory=True)
+    host.copy_(packed, non_blocking=True)
+    cur.synchronize()                                                                                      # sync 2
+    raw = host.numpy().view(np.uint8)
+    ends = np.cumsum(nw_all) * 4
+    flat, a = [], 0
+    for e in ends.tolist():
+        flat.append(raw[a:e].tobytes())
+        a = e
+    out, a = [], 0
+    it = iter(counts)
+    for b in batches:
+        if b.n_words.numel():
+            c = next(it)
+            out.append(flat[a:a + c])
+            a += c
+        else:
+            out.append([])
+    return out
 
 
 def encode(table: CdfTable, symbols: torch.Tensor, indexes: torch.Tensor) -> EncodedBatch:
@@ -201,5 +272,11 @@ def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, sta
 
 def check_status(statuses, what="rANS decode"):
     """Deferred check of the status tensors collected with ``status_out`` (synchronises)."""
+    statuses = [st for st in statuses if st.numel()]
+    if not statuses:
+        return
+    allst = to_host(torch.cat([st.reshape(-1) for st in statuses]))
+    if int(allst.abs().max()) == 0:
+        return
     for st in statuses:
         _raise_status(st, what)

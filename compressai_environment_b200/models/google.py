@@ -220,7 +220,9 @@ class ScaleHyperprior(CompressionModel):
         pool = self.__dict__.setdefault("_stream_pool", {})
         st = pool.get(str(device))
         if st is None:
-            st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device),
+            # "hyp" is high priority: its kernels are tiny and gate the start of the long y decodes, so they must
+            # not queue behind whole analysis / synthesis grids of other requests in the block scheduler
+            st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device, priority=int(__import__("os").environ.get("CAI_HYP_PRIO", "-1"))),
                   "syn": torch.cuda.Stream(device=device),
                   "pool": [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.coder_stream_pool)],
                   "next": 0}
@@ -276,11 +278,9 @@ class ScaleHyperprior(CompressionModel):
     def compress(self, x):
         out = self.compress_to_device(x)
         y_encs, z_encs = out["strings"]
-        ys, zs = [], []
-        for ye, ze in zip(y_encs, z_encs):
-            with torch.cuda.stream(ye.stream):
-                ys += ye.to_bytes()
-                zs += ze.to_bytes()
+        lists = coder.batches_to_bytes(list(y_encs) + list(z_encs))  # two host syncs for the whole request
+        ys = [s for lst in lists[:len(y_encs)] for s in lst]
+        zs = [s for lst in lists[len(y_encs):] for s in lst]
         return {"strings": [ys, zs], "shape": out["shape"]}
 
     @torch.no_grad()

@@ -16,4 +16,4 @@ def step():
 with torch.no_grad():
     step(); print("h2d, compress, decompress, d2h (ms):", step())
     pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
-    pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+    pstats.Stats(pr).sort_stats("tottime").print_stats(32)
