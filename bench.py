@@ -30,7 +30,12 @@ sys.path.insert(0, ROOT)
 
 H, W = 512, 768
 N_CH, M_CH = 128, 192
-GAIN_Y, GAIN_S = 64.0, 256.0
+# Random-init weights give near-zero latents (every symbol 0, every scale at the table floor).  The last analysis layer
+# and the last hyper-synthesis layer are scaled so that the synthetic stream lands on the operating point of the
+# TRAINED q4 model: gains (4, 32) -> 0.50 bits per pixel (trained bmshj2018-hyperprior q4 on Kodak: ~0.47 bpp),
+# 0.45 bits per y symbol, scale indexes 0..21.  ``--gain-y 64 --gain-s 256`` is the former stress setting:
+# 9.3 bpp, 35% of the y symbols escape-coded (reported in DESIGN.md as the heavy-stream case).
+GAIN_Y, GAIN_S = 4.0, 32.0
 METRIC = "compress+decompress throughput, bmshj2018-hyperprior q4, 768x512 images"
 UNIT = "MP/s"
 
@@ -461,9 +466,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gain-y", type=float, default=GAIN_Y, help="scale of the last g_a layer (stream rate, see GAIN_Y)")
+    ap.add_argument("--gain-s", type=float, default=GAIN_S, help="scale of the last h_s layer")
     ap.add_argument("--inflight", type=int, default=2, help="steps in flight (user streams) in the device-timed loop")
     ap.add_argument("--e2e-inflight", type=int, default=3, help="requests in flight (host threads) in the e2e loop")
     args = ap.parse_args()
+    globals().update(GAIN_Y=args.gain_y, GAIN_S=args.gain_s)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -250,34 +250,38 @@ rans_encode_kernel(const unsigned char *__restrict__ blob, uint32_t enc_bytes, c
       for (int l = nvalid - 1; l >= 0; --l) {
         const uint4 e = e_next;
         if (l > 0) e_next = *reinterpret_cast<const uint4 *>(pp + (l - 1));  // hide the LDS latency of the next step
-        if (!(e.y & 0x80000000u)) {
-          // escape: the entry list read backwards is payload nibbles MSB..LSB, then the count nibble, i.e. the
-          // (nb+1)-nibble integer V = raw << 4 | nb pushed MSB first.  The reference renormalises before a nibble
-          // iff x >= 2^59 (rans_interface.cpp:69-87); with L = bitlen(x) exactly J = (59 - L) / 4 + 1 nibbles fit
-          // before that happens, so nibbles are pushed in groups (at most 3 rounds) instead of one by one.
-          const uint32_t raw = rr[l];
-          const int nb = raw ? ((35 - __clz(raw)) >> 2) : 0;
-          const uint64_t V = (static_cast<uint64_t>(raw) << 4) | static_cast<uint32_t>(nb);
-          int rem = nb + 1;
-          while (rem > 0) {
-            const int L = 64 - __clzll(x);
-            if (L > 59) {
-              em.push(static_cast<uint32_t>(x));
-              x >>= 32;
-              continue;
+        // Rans64EncPut (rans64.h:77-93): renormalise iff x >= freq << 47, then x = x + bias + (x / freq) * (2^16 - freq).
+        // Common case: ordinary symbol, no renormalisation -> straight-line code behind ONE branch.
+        if (!(e.y & 0x80000000u) || static_cast<uint32_t>(x >> 32) >= e.w) {
+          if (!(e.y & 0x80000000u)) {
+            // escape: the entry list read backwards is payload nibbles MSB..LSB, then the count nibble, i.e. the
+            // (nb+1)-nibble integer V = raw << 4 | nb pushed MSB first.  The reference renormalises before a nibble
+            // iff x >= 2^59 (rans_interface.cpp:69-87); with L = bitlen(x) exactly J = (59 - L) / 4 + 1 nibbles fit
+            // before that happens, so nibbles are pushed in groups (at most 3 rounds) instead of one by one.
+            const uint32_t raw = rr[l];
+            const int nb = raw ? ((35 - __clz(raw)) >> 2) : 0;
+            const uint64_t V = (static_cast<uint64_t>(raw) << 4) | static_cast<uint32_t>(nb);
+            int rem = nb + 1;
+            while (rem > 0) {
+              const int L = 64 - __clzll(x);
+              if (L > 59) {
+                em.push(static_cast<uint32_t>(x));
+                x >>= 32;
+                continue;
+              }
+              const int J = ((59 - L) >> 2) + 1;
+              const int c = J < rem ? J : rem;
+              const uint64_t part = (V >> (4 * (rem - c))) & ((1ull << (4 * c)) - 1ull);
+              x = (x << (4 * c)) | part;
+              rem -= c;
             }
-            const int J = ((59 - L) >> 2) + 1;
-            const int c = J < rem ? J : rem;
-            const uint64_t part = (V >> (4 * (rem - c))) & ((1ull << (4 * c)) - 1ull);
-            x = (x << (4 * c)) | part;
-            rem -= c;
+          }
+          const uint32_t xh = static_cast<uint32_t>(x >> 32);
+          if (xh >= e.w) {
+            em.push(static_cast<uint32_t>(x));
+            x = static_cast<uint64_t>(xh);
           }
         }
-        // Rans64EncPut (rans64.h:77-93): renormalise iff x >= freq << 47, then x = x + bias + (x / freq) * (2^16 - freq)
-        const uint32_t xh = static_cast<uint32_t>(x >> 32);
-        const bool rn = xh >= e.w;
-        em.push_if(rn, static_cast<uint32_t>(x));
-        x = rn ? static_cast<uint64_t>(xh) : x;
         const uint64_t m = (static_cast<uint64_t>(e.y | 0x80000000u) << 32) | e.x;
         const uint32_t shift = e.z >> 20;
         const uint32_t bias = e.z & 0xFFFFFu;
@@ -423,73 +427,82 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
         const int32_t maxv = static_cast<int32_t>(d.y);
         const uint32_t cf = static_cast<uint32_t>(x) & 0xFFFFu;
         const uint2 e = lut[d.w + (cf >> lut_shift)];
-        uint32_t start = e.x & 0xFFFFu;
-        uint32_t freq = e.x >> 16;
-        int32_t s = static_cast<int32_t>(e.y);
-        if (freq == 0) {
-          // bucket spans several symbols: warp-cooperative forward search from s.  Lane i tests symbol s + i
-          // (cdf[s+i] <= cf < cdf[s+i+1]); exactly one lane can hit, and a max-reduction broadcasts its
-          // (freq, start) pair without a second round of dependent shared-memory loads.
-          for (;;) {
-            const int32_t cand = s + lane;
-            uint32_t packed = 0;
-            if (cand <= maxv) {
-              const uint32_t c_lo = cdf16[d.x + cand];
-              const uint32_t c_hi = (cand == maxv) ? 0x10000u : static_cast<uint32_t>(cdf16[d.x + cand + 1]);
-              if (c_lo <= cf && cf < c_hi) packed = ((c_hi - c_lo) << 16) | c_lo;
-            }
-            const uint32_t win = __reduce_max_sync(0xffffffffu, packed);
-            if (win) {
-              s += __ffs(__ballot_sync(0xffffffffu, packed != 0)) - 1;
-              start = win & 0xFFFFu;
-              freq = win >> 16;
-              break;
-            }
-            s += 32;
-            if (s > maxv) {  // malformed table: stay in bounds, keep the chain defined
-              s = maxv < 0 ? 0 : maxv;
-              start = cdf16[d.x + s];
-              freq = 1;
-              break;
+        // Fast path (the common case on real streams): the bucket names one ordinary symbol (the table builder
+        // marks buckets of the escape symbol as "search", freq field 0) and the new state needs no refill.  It is
+        // straight-line code with ONE branch; every rare event takes the general path below.
+        const uint64_t xn = static_cast<uint64_t>(e.x >> 16) * (x >> 16) + (cf - (e.x & 0xFFFFu));
+        int32_t v = static_cast<int32_t>(e.y);
+        if ((e.x >> 16) != 0u && (xn >> 31) != 0ull) {
+          x = xn;
+        } else {
+          uint32_t start = e.x & 0xFFFFu;
+          uint32_t freq = e.x >> 16;
+          int32_t s = static_cast<int32_t>(e.y);
+          if (freq == 0) {
+            // bucket spans several symbols: warp-cooperative forward search from s.  Lane i tests symbol s + i
+            // (cdf[s+i] <= cf < cdf[s+i+1]); exactly one lane can hit, and a max-reduction broadcasts its
+            // (freq, start) pair without a second round of dependent shared-memory loads.
+            for (;;) {
+              const int32_t cand = s + lane;
+              uint32_t packed = 0;
+              if (cand <= maxv) {
+                const uint32_t c_lo = cdf16[d.x + cand];
+                const uint32_t c_hi = (cand == maxv) ? 0x10000u : static_cast<uint32_t>(cdf16[d.x + cand + 1]);
+                if (c_lo <= cf && cf < c_hi) packed = ((c_hi - c_lo) << 16) | c_lo;
+              }
+              const uint32_t win = __reduce_max_sync(0xffffffffu, packed);
+              if (win) {
+                s += __ffs(__ballot_sync(0xffffffffu, packed != 0)) - 1;
+                start = win & 0xFFFFu;
+                freq = win >> 16;
+                break;
+              }
+              s += 32;
+              if (s > maxv) {  // malformed table: stay in bounds, keep the chain defined
+                s = maxv < 0 ? 0 : maxv;
+                start = cdf16[d.x + s];
+                freq = 1;
+                break;
+              }
             }
           }
-        }
-        x = static_cast<uint64_t>(freq) * (x >> 16) + (cf - start);
-        if (x < (1ull << 31)) x = (x << 32) | wf.take();
-        int32_t v = s;
-        if (s == maxv) {
-          // bypass / escape decoding (rans_interface.cpp:256-278).  Count nibble(s) one at a time, then the
-          // payload nibbles in groups: with L = bitlen(x), the reference refills after pop number
-          // ceil((L - 31) / 4) (that pop leaves x < 2^31), so that many nibbles can be taken at once.
-          uint32_t t = static_cast<uint32_t>(x) & 15u;
-          x >>= 4;
+          x = static_cast<uint64_t>(freq) * (x >> 16) + (cf - start);
           if (x < (1ull << 31)) x = (x << 32) | wf.take();
-          int32_t nb = static_cast<int32_t>(t);
-          while (t == 15u) {
-            t = static_cast<uint32_t>(x) & 15u;
+          v = s;
+          if (s == maxv) {
+            // bypass / escape decoding (rans_interface.cpp:256-278).  Count nibble(s) one at a time, then the
+            // payload nibbles in groups: with L = bitlen(x), the reference refills after pop number
+            // ceil((L - 31) / 4) (that pop leaves x < 2^31), so that many nibbles can be taken at once.
+            uint32_t t = static_cast<uint32_t>(x) & 15u;
             x >>= 4;
             if (x < (1ull << 31)) x = (x << 32) | wf.take();
-            nb += static_cast<int32_t>(t);
+            int32_t nb = static_cast<int32_t>(t);
+            while (t == 15u) {
+              t = static_cast<uint32_t>(x) & 15u;
+              x >>= 4;
+              if (x < (1ull << 31)) x = (x << 32) | wf.take();
+              nb += static_cast<int32_t>(t);
+            }
+            uint64_t acc = 0;
+            int done = 0;
+            int rem = nb;
+            while (rem > 0) {
+              const int L = 64 - __clzll(x);
+              int js = (L - 31 + 3) >> 2;
+              if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
+              const int c = rem < js ? rem : js;
+              const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
+              x >>= 4 * c;
+              if (done < 8) acc |= bits << (4 * done);
+              done += c;
+              rem -= c;
+              if (c == js) x = (x << 32) | wf.take();
+            }
+            const uint32_t raw = static_cast<uint32_t>(acc);
+            const int32_t sraw = static_cast<int32_t>(raw);
+            v = sraw >> 1;
+            v = (sraw & 1) ? (-v - 1) : (v + maxv);
           }
-          uint64_t acc = 0;
-          int done = 0;
-          int rem = nb;
-          while (rem > 0) {
-            const int L = 64 - __clzll(x);
-            int js = (L - 31 + 3) >> 2;
-            if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
-            const int c = rem < js ? rem : js;
-            const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
-            x >>= 4 * c;
-            if (done < 8) acc |= bits << (4 * done);
-            done += c;
-            rem -= c;
-            if (c == js) x = (x << 32) | wf.take();
-          }
-          const uint32_t raw = static_cast<uint32_t>(acc);
-          const int32_t sraw = static_cast<int32_t>(raw);
-          v = sraw >> 1;
-          v = (sraw & 1) ? (-v - 1) : (v + maxv);
         }
         if (lane == l) myout = v + static_cast<int32_t>(d.z);
       }

@@ -128,7 +128,10 @@ __global__ void table_lut_kernel(BlobHeader hdr, unsigned char *__restrict__ blo
       const uint32_t start = row[lo];
       const uint32_t next = (lo + 1 >= nsym) ? 65536u : static_cast<uint32_t>(row[lo + 1]);
       e.y = static_cast<uint32_t>(lo);
-      if (next > cf1 && next > start) e.x = start | ((next - start) << 16);
+      // a bucket is "direct" (freq field != 0) only if it names ONE ORDINARY symbol; buckets that straddle a symbol
+      // boundary, and buckets of the escape symbol (the last one), are left as "search from e.y" so that the
+      // decoder's fast path needs a single test
+      if (next > cf1 && next > start && lo != nsym - 1) e.x = start | ((next - start) << 16);
     }
     lut[b] = e;
   }
@@ -233,8 +236,12 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
   t->Lmax = Lmax;
   t->lut_shift = h.lut_shift;
   t->lut_buckets = h.lut_buckets;
-  t->in_smem = in_smem;
-  t->enc_in_smem = static_cast<int64_t>(h.enc_bytes) <= budget;
+  // CAI_TABLE_SMEM_KB: tables larger than this stay in global memory (L1 / L2) even if they would fit the CTA's
+  // shared memory -- a coder CTA that stages a big table keeps the transform kernels' CTAs off its SM.
+  int64_t cap = budget;
+  if (const char *ov = getenv("CAI_TABLE_SMEM_KB")) cap = static_cast<int64_t>(atoi(ov)) * 1024;
+  t->in_smem = in_smem && static_cast<int64_t>(h.total_bytes) <= cap;
+  t->enc_in_smem = static_cast<int64_t>(h.enc_bytes) <= budget && static_cast<int64_t>(h.enc_bytes) <= cap;
   t->device = dp.device;
   *out = t;
   return CAI_OK;

@@ -10,6 +10,8 @@ ap.add_argument("--B", type=int, default=4096)
 ap.add_argument("--n", type=int, default=65536)
 ap.add_argument("--t", type=float, default=1.0)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--max-idx", type=int, default=64, help="scale indexes drawn from [0, max-idx): 22 ~ the bench workload")
+ap.add_argument("--no-quant", action="store_true")
 a = ap.parse_args()
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "cdf.npz"))
 dev = torch.device("cuda")
@@ -17,7 +19,7 @@ table = coder.CdfTable(*(torch.from_numpy(g[k]).to(dev) for k in ("gc_cdf", "gc_
 print(table.info())
 gen = torch.Generator(device=dev).manual_seed(1234)
 tab = torch.from_numpy(g["gc_scale_table"]).to(dev)
-idx = torch.randint(0, 64, (a.B, a.n), generator=gen, device=dev, dtype=torch.int32)
+idx = torch.randint(0, a.max_idx, (a.B, a.n), generator=gen, device=dev, dtype=torch.int32)
 sym = torch.round(torch.randn((a.B, a.n), generator=gen, device=dev) * tab[idx.long()] * a.t).to(torch.int32)
 def timed(fn, iters):
     fn(); torch.cuda.synchronize()
@@ -35,6 +37,7 @@ words, wb, keep = coder.strings_to_device(strings, dev); torch.cuda.synchronize(
 ms, dec = timed(lambda: coder.decode(table, None, idx, device_words=(words, wb)), a.iters)
 print(f"decode: {ms:.3f} ms  {nsym/ms/1e6:.2f} Gsym/s  algGB/s={(8*nsym+4*nw)/ms/1e6:.1f}")
 assert torch.equal(dec, sym)
+if a.no_quant: sys.exit(0)
 y = torch.randn((a.B, a.n), generator=gen, device=dev) * 5
 sc = torch.exp(torch.rand((a.B, a.n), generator=gen, device=dev) * 8 - 3)
 ms, _ = timed(lambda: kernels.gc_quantize_index(y.view(a.B, a.n, 1), sc.view(a.B, a.n, 1), None, tab, 0.11), a.iters)
