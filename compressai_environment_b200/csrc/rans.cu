@@ -79,7 +79,7 @@ struct __align__(16) DecParam {
 };
 
 constexpr int kEncWarpBytes = 2 * 32 * (sizeof(EncParam) + sizeof(uint32_t));  // 1280
-constexpr int kDecWarpBytes = 2 * 32 * sizeof(DecParam);                       // 1024
+constexpr int kDecWarpBytes = 2 * 32 * (sizeof(DecParam) + sizeof(int32_t));     // 1280: parameter ring + index staging
 
 template <bool kSmem>
 struct TableView {
@@ -391,17 +391,25 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
     }
 
     const int64_t nchunks = (n + 31) >> 5;
-    int32_t r_idx = 0;
+    // Index prefetch, one chunk ahead, with cp.async into shared memory.  (As a register prefetch the load's
+    // scoreboard wait landed on the first branch of the symbol loop: ~13% of the kernel waiting for DRAM.)
+    int32_t *ibuf = reinterpret_cast<int32_t *>(pbuf + 64);
     auto stage1 = [&](int64_t j) {
       const int64_t i = (j << 5) + lane;
-      r_idx = (i < n) ? __ldg(idx + i) : 0;
+      int32_t *dst_s = ibuf + static_cast<int>(j & 1) * 32 + lane;
+      if (i < n)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_s)), "l"(idx + i) : "memory");
+      else
+        *dst_s = 0;
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (nchunks > 0) stage1(0);
 
     for (int64_t j = 0; j < nchunks; ++j) {
       DecParam *pp = pbuf + static_cast<int>(j & 1) * 32;
       {
-        int32_t k = r_idx;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        int32_t k = ibuf[static_cast<int>(j & 1) * 32 + lane];
         if (k < 0 || k >= K) {
           if ((j << 5) + lane < n) st = CAI_S_BAD_INDEX;
           k = 0;

@@ -209,7 +209,7 @@ class ScaleHyperprior(CompressionModel):
     # because nothing here synchronises the host, the analysis of the NEXT call overlaps this call's decode wait.
     max_streams = 8
 
-    coder_stream_pool = 24
+    coder_stream_pool = int(__import__("os").environ.get("CAI_CODER_STREAMS", "16"))
 
     def _streams(self, device, n):
         """Shared, in-order transform streams -- "ana" (analysis), "hyp" (hyper-synthesis + index kernels: short work
