@@ -38,7 +38,7 @@ class ConvDesc(Structure):
                                          "out_lo", "sq_hi", "sq_lo", "abs_hi", "abs_lo")]
                 + [(n, c_int32) for n in ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "Hp", "Wp", "os", "o0y", "o0x", "is_",
                                           "ntaps", "BN", "epilogue")]
-                + [("clamp_lo", c_float), ("clamp_hi", c_float), ("dy", c_int8 * 32), ("dx", c_int8 * 32),
+                + [("clamp_lo", c_float), ("clamp_hi", c_float), ("dy", c_int8 * 32), ("dx", c_int8 * 32), ("glen", c_int8 * 32),
                    ("gdn_w", c_void_p), ("gdn_beta", c_void_p), ("gdn_mode", c_int32)])
 
 

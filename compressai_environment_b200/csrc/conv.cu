@@ -71,6 +71,7 @@ struct ConvKernelParams {
   int gdn_mode;                      // 1 GDN, 2 IGDN
   int debug;                         // experiment bitmask: 1 skip A loads, 2 skip B loads, 4 skip MMAs
   int8_t dy[kMaxTaps], dx[kMaxTaps];
+  int8_t glen[kMaxTaps];             // tap group lengths (taps of a group share dy; dx differ by multiples of `is`)
 };
 
 __device__ __forceinline__ void spin_fail() {
@@ -95,7 +96,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -316,33 +317,38 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       }
     }
 
-    // Per-tap state (recomputed only when the tap changes, i.e. every kchunks k-steps): element offset of the
-    // tap's input pixel for each of the 4 rows, 0 / 16 byte count for padding.  Per k-step only the channel chunk
-    // offset (kc * kBK elements) is added, so the steady-state cost is a handful of instructions per cp.async.
+    // Per-GROUP state (recomputed only when the tap group changes): element offset of the input pixel for
+    // (dy of the group, dx = 0) for each of this thread's rows, and 0 / 16 bytes for rows whose input row is padding.
+    // k-steps walk  group -> channel chunk -> tap in group: the taps of a group read the same activation lines
+    // shifted by one pixel, so all but the first are L1 hits instead of L2 round trips.  Per k-step only
+    // dx * Cin + kc * kBK is added and the column bound is checked.
     int64_t tap_off[kLoadIters];
     uint32_t tap_bytes[kLoadIters];
-    int cur_t = 0, cur_kc = 0;
-    auto set_tap = [&](int t) {
-      const int dy = p.dy[t], dx = p.dx[t];
+    int cur_t0 = 0, cur_g = 0, cur_gl = p.glen[0], cur_ti = 0, cur_kc = 0;
+    auto set_group = [&](int t0) {
+      const int dy = p.dy[t0];
 #pragma unroll
       for (int it = 0; it < kLoadIters; ++it) {
-        const int iy = ld_iy[it] + dy, ix = ld_ix[it] + dx;
-        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        tap_off[it] = ok ? ((ld_img[it] + static_cast<int64_t>(iy) * p.W + ix) * p.Cin + lc * 8) : 0;
+        const int iy = ld_iy[it] + dy;
+        const bool ok = iy >= 0 && iy < p.H;
+        tap_off[it] = ok ? ((ld_img[it] + static_cast<int64_t>(iy) * p.W + ld_ix[it]) * p.Cin + lc * 8) : 0;
         tap_bytes[it] = ok ? 16u : 0u;
       }
     };
-    set_tap(0);
+    set_group(0);
 
     auto issue = [&](int ks, int s) {  // must be called with ks = 0, 1, 2, ... in order; s = ks mod stages
       unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
       const int kbase = cur_kc * kBK;
       const bool k_ok = kbase + lc * 8 < p.Cin;
+      const int dx = p.dx[cur_t0 + cur_ti];
+      const int64_t koff = static_cast<int64_t>(dx) * p.Cin + kbase;
 #pragma unroll
       for (int it = 0; it < kLoadIters; ++it) {
         if (p.debug & 1) break;
-        const uint32_t nbytes = k_ok ? tap_bytes[it] : 0u;
-        const int64_t off = nbytes ? tap_off[it] + kbase : 0;
+        const bool x_ok = static_cast<uint32_t>(ld_ix[it] + dx) < static_cast<uint32_t>(p.W);
+        const uint32_t nbytes = (k_ok && x_ok) ? tap_bytes[it] : 0u;
+        const int64_t off = nbytes ? tap_off[it] + koff : 0;
         cp_async16(sa + ld_so[it], p.a_hi + off, nbytes);
         cp_async16(sa + a_plane + ld_so[it], p.a_lo + off, nbytes);
       }
@@ -354,9 +360,17 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           tma_bulk_g2s(sa + 2 * a_plane, wbase + static_cast<size_t>(ks) * (2 * b_plane), 2 * b_plane, &full_bar[s]);
         }
       }
-      if (++cur_kc == p.kchunks) {
-        cur_kc = 0;
-        if (++cur_t < p.ntaps) set_tap(cur_t);
+      if (++cur_ti == cur_gl) {
+        cur_ti = 0;
+        if (++cur_kc == p.kchunks) {
+          cur_kc = 0;
+          cur_t0 += cur_gl;
+          ++cur_g;
+          if (cur_t0 < p.ntaps) {
+            cur_gl = p.glen[cur_g];
+            set_group(cur_t0);
+          }
+        }
       }
     };
 
@@ -997,10 +1011,32 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
     p.dy[t] = d->dy[t];
     p.dx[t] = d->dx[t];
   }
+  {  // tap groups: all zero = one tap per group; otherwise lengths must cover ntaps and a group shares dy
+    int covered = 0;
+    for (int g = 0; g < kMaxTaps; ++g) p.glen[g] = 0;
+    if (d->glen[0] == 0) {
+      for (int t = 0; t < d->ntaps; ++t) p.glen[t] = 1;
+      covered = d->ntaps;
+    } else {
+      for (int g = 0; g < kMaxTaps && covered < d->ntaps; ++g) {
+        const int n = d->glen[g];
+        CAI_CHECK_ARG(n >= 1 && covered + n <= d->ntaps, "cai_conv_gemm: bad tap group length glen[%d]=%d", g, n);
+        for (int t = covered + 1; t < covered + n; ++t)
+          CAI_CHECK_ARG(d->dy[t] == d->dy[covered], "cai_conv_gemm: taps of group %d do not share dy", g);
+        p.glen[g] = static_cast<int8_t>(n);
+        covered += n;
+      }
+    }
+    CAI_CHECK_ARG(covered == d->ntaps, "cai_conv_gemm: tap groups cover %d of %d taps", covered, d->ntaps);
+  }
   const size_t stage_bytes = 2 * static_cast<size_t>((kBK / 8) * kLboA) + 2 * static_cast<size_t>(d->BN) * kBK * 2;
   // two CTAs per SM (one CTA's epilogue overlaps the other's main loop): each gets half of the shared memory
   int stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) / 2 - 2048) / stage_bytes);
   if (stages > 4) stages = 4;
+  // Multi-tap layers re-read each activation line from L1 for the later taps of a group: a shallower ring leaves
+  // more of the unified L1/shared memory to the cache, which is worth more than the third stage (measured on the
+  // 128->128 k5 s2 layer: 2.19 ms with 3 stages, 2.08 ms with 2).
+  if (d->ntaps > 1 && stages > 2) stages = 2;
   if (stages < 2) stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes) >= 2 ? 2 : stages;
   if (const char *ov = getenv("CAI_CONV_STAGES")) {  // tuning override (experiments only)
     const int v = atoi(ov);
@@ -1037,10 +1073,14 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   if (getenv("CAI_CONV_GENERIC")) kind = 0;
   const dim3 grid(static_cast<unsigned>(mt), static_cast<unsigned>(nt));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  int carveout = -1;  // CAI_CONV_CARVEOUT: preferred shared-memory carve-out in percent (experiments only)
+  if (const char *ov = getenv("CAI_CONV_CARVEOUT")) carveout = atoi(ov);
 #define CAI_LAUNCH_KIND(K)                                                                                           \
   do {                                                                                                               \
     CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
                                   static_cast<int>(smem)));                                                          \
+    if (carveout >= 0)                                                                                               \
+      CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout)); \
     conv_gemm_kernel<K><<<grid, kConvThreads, smem, st>>>(p);                                                       \
   } while (0)
   switch (kind) {

@@ -172,9 +172,33 @@ def _choose_bn(cout: int) -> int:
     return 128
 
 
-def pack_weights(w_taps: Tensor, bn: int) -> Tensor:
-    """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][T * kchunks][hi | lo][BN x 32 bf16] in the UMMA canonical
-    K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2)."""
+class Taps(list):
+    """List of (dy, dx) taps in launch order plus ``glen``: lengths of the consecutive tap groups whose input pixel
+    sets coincide up to a one-pixel shift (same dy, dx congruent modulo the input stride).  The kernel walks
+    k-steps as  for group: for channel chunk: for tap in group,  so the taps of a group re-read from L1 the
+    activation lines the first one brought in from L2."""
+    glen: List[int] = None
+
+
+def _grouped(taps, rows, step: int):
+    """Reorder ``taps`` (and the parallel weight slices ``rows``) into groups; returns (Taps, reordered rows)."""
+    keys = {}
+    for i, (dy, dx) in enumerate(taps):
+        keys.setdefault((dy, dx % step), []).append(i)
+    order, glen = [], []
+    for _, idxs in sorted(keys.items()):
+        idxs = sorted(idxs, key=lambda i: taps[i][1])
+        order += idxs
+        glen.append(len(idxs))
+    out = Taps(taps[i] for i in order)
+    out.glen = glen
+    return out, [rows[i] for i in order]
+
+
+def pack_weights(w_taps: Tensor, bn: int, glen=None) -> Tensor:
+    """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][k-step][hi | lo][BN x 32 bf16] in the UMMA canonical
+    K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2).
+    k-step order: for tap group (``glen``, default one tap per group): for channel chunk: for tap in group."""
     T, cout, cin = w_taps.shape
     nt = (cout + bn - 1) // bn
     kc = (cin + _BK - 1) // _BK
@@ -183,8 +207,16 @@ def pack_weights(w_taps: Tensor, bn: int) -> Tensor:
     wp = wp.view(T, nt, bn // 8, 8, kc, _BK // 8, 8).permute(1, 0, 4, 5, 2, 3, 6)  # nt, T, kc, k8, r8, r%8, k%8
     hi = wp.to(torch.bfloat16)
     lo = (wp - hi.float()).to(torch.bfloat16)
-    packed = torch.stack([hi, lo], dim=3).contiguous()  # nt, T, kc, 2, k8, r8, r%8, k%8
-    return packed.view(torch.uint8).reshape(-1)
+    packed = torch.stack([hi, lo], dim=3)  # nt, T, kc, 2, k8, r8, r%8, k%8
+    if glen is not None and any(g > 1 for g in glen):
+        assert sum(glen) == T
+        sched, t0 = [], 0
+        for g in glen:
+            sched += [t * kc + c for c in range(kc) for t in range(t0, t0 + g)]
+            t0 += g
+        flat = packed.reshape(nt, T * kc, *packed.shape[3:])
+        packed = flat[:, torch.tensor(sched, device=flat.device)]
+    return packed.contiguous().view(torch.uint8).reshape(-1)
 
 
 class _Layer:
@@ -217,9 +249,12 @@ def _prep_conv(m: "Conv2d") -> _Layer:
     else:
         wt = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
         taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
+        taps, rows = _grouped(taps, list(wt.unbind(0)), s)
+        wt = torch.stack(rows, 0)
         cp, kp = _c16(cout), _c16(cin)
         bn = _choose_bn(cp)
-        lay = _Layer("conv", pack_weights(_pad_taps(wt, cp, kp), bn), _pad_vec(m.bias, cp), [taps], bn, kp, cp, (k, s, p))
+        lay = _Layer("conv", pack_weights(_pad_taps(wt, cp, kp), bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
+                     (k, s, p))
     m._packed = (key, lay)
     return lay
 
@@ -252,8 +287,10 @@ def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
                             continue
                         taps.append(((py + p - ky) // s, (px + p - kx) // s))
                         ws.append(w[:, :, ky, kx].t())  # [cout, cin]
+                if ws:
+                    taps, ws = _grouped(taps, ws, 1)
                 phases.append(taps)
-                blobs.append(pack_weights(_pad_taps(torch.stack(ws, 0), cp, kp), bn) if ws else None)
+                blobs.append(pack_weights(_pad_taps(torch.stack(ws, 0), cp, kp), bn, taps.glen) if ws else None)
         lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op))
     m._packed = (key, lay)
     return lay
@@ -300,6 +337,8 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
     d.clamp_lo, d.clamp_hi = (clamp if clamp is not None else (0.0, 0.0))
     for t, (dy, dx) in enumerate(taps):
         d.dy[t], d.dx[t] = dy, dx
+    for g, n in enumerate(getattr(taps, "glen", None) or [1] * len(taps)):
+        d.glen[g] = n
     with torch.cuda.device(a.hi.device):
         if TIMING is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -227,7 +227,11 @@ int cai_eb_logits(const float *x, const float *tparams, const int32_t *filters_h
  *     D[pixel, co] = sum_{t < ntaps} sum_{ci} A[n, i*is + dy[t], j*is + dx[t], ci] * Wt[co, t, ci]
  * (out-of-range input pixels read as zero) and writes pixel (i*os + o0y, j*os + o0x) of the output.
  * w_packed holds the weights pre-split and pre-tiled by the host layer (see transforms.py:pack_weights):
- * [n_tile][kstep = t * kchunks + kc][hi | lo][BN x 32 bf16 in UMMA canonical K-major order] (k-step = 32 channels).
+ * [n_tile][k-step][hi | lo][BN x 32 bf16 in UMMA canonical K-major order] (k-step = 32 channels of one tap).
+ * k-step order: taps come in groups of glen[g] consecutive taps that share dy and whose dx differ by multiples of
+ * `is` (their input pixel sets coincide up to a shift, so the later taps of a group hit L1); the kernel walks
+ *   for group g: for channel chunk kc: for tap t in group g
+ * and w_packed is laid out in that order.  glen[] all zero = one tap per group (k-step = t * kchunks + kc).
  * epilogue: 0 linear, 1 ReLU, 2 LeakyReLU(0.01), 3 GDN  out = aux * rsqrt(D + bias),
  *           4 IGDN out = aux * sqrt(D + bias)   (aux given as split planes shaped like the output).
  * Outputs (any subset): out_f32 fp32 NHWC, out_hi/lo split planes, sq_hi/lo planes of out^2 (the GDN
@@ -247,6 +251,7 @@ typedef struct cai_conv_desc {
   int32_t epilogue;
   float clamp_lo, clamp_hi;  /* clamp applied when clamp_lo < clamp_hi */
   int8_t dy[32], dx[32];
+  int8_t glen[32];           /* tap group lengths, sum = ntaps (see above) */
   /* Fused GDN / IGDN (compressai/layers/gdn.py:77-92) as a second in-kernel GEMM: with v = D + bias,
    * out = v * rsqrt(gamma . v^2 + beta) (gdn_mode 1) or v * sqrt(...) (gdn_mode 2).  gdn_w = gamma packed like
    * w_packed with one tap ([kchunk][hi | lo][Cout x 32 bf16]); needs BN == Cout <= 256 and epilogue == 0.
