@@ -64,3 +64,39 @@ def test_ddp_gradient_allreduce_gloo(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "DDP_OK" in out.stdout
+
+
+def test_tap_groups_and_weight_schedule_cpu():
+    """Host-side k-step schedule of the transform kernel (pure torch, no GPU): taps are grouped by (dy, dx mod
+    stride) and the packed weight blob follows  group -> channel chunk -> tap in group  (include/cai_b200.h)."""
+    import torch
+    from compressai_environment_b200.transforms import _grouped, pack_weights, _BK
+
+    k, s, p = 5, 2, 2
+    taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
+    rows = list(range(len(taps)))
+    g, order = _grouped(taps, rows, s)
+    assert sorted(order) == rows and sum(g.glen) == 25 and g.glen == [3, 2] * 5
+    t0 = 0
+    for n in g.glen:
+        grp = g[t0:t0 + n]
+        assert len({dy for dy, _ in grp}) == 1 and len({dx % s for _, dx in grp}) == 1
+        assert [dx for _, dx in grp] == sorted(dx for _, dx in grp)
+        t0 += n
+    g1, _ = _grouped([(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)], list(range(9)), 1)
+    assert g1.glen == [3, 3, 3]
+
+    # blob order: tile (g, kc, t) must hold tap t's channels [kc*32, kc*32+32)
+    T, cout, cin, bn = 5, 16, 64, 16
+    w = torch.arange(T * cout * cin, dtype=torch.float32).reshape(T, cout, cin) / 7.0
+    glen = [3, 2]
+    blob = pack_weights(w, bn, glen).view(torch.bfloat16).reshape(-1, 2, _BK // 8, bn // 8, 8, 8)  # kstep, hi/lo, k8, r8, r, k
+    sched = [(t, c) for t0, n in ((0, 3), (3, 2)) for c in range(cin // _BK) for t in range(t0, t0 + n)]
+    assert blob.shape[0] == len(sched)
+    for ks, (t, c) in enumerate(sched):
+        tile = blob[ks, 0].permute(1, 2, 0, 3).reshape(bn, _BK).float()        # [row, k]
+        ref = w[t, :, c * _BK:(c + 1) * _BK].to(torch.bfloat16).float()
+        assert torch.equal(tile, ref), (ks, t, c)
+    # default (no groups) keeps tap-major order
+    blob0 = pack_weights(w, bn).view(torch.bfloat16).reshape(-1, 2, _BK // 8, bn // 8, 8, 8)
+    assert torch.equal(blob0[1, 0].permute(1, 2, 0, 3).reshape(bn, _BK).float(), w[0, :, _BK:2 * _BK].to(torch.bfloat16).float())
