@@ -446,7 +446,12 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
           uint32_t start = e.x & 0xFFFFu;
           uint32_t freq = e.x >> 16;
           int32_t s = static_cast<int32_t>(e.y);
-          if (freq == 0) {
+          if (freq == 0 && (e.y & 0x80000000u)) {
+            // the whole bucket lies inside the escape symbol (table.cu marks it): start is in the entry
+            s = maxv;
+            start = e.y & 0xFFFFu;
+            freq = 0x10000u - start;
+          } else if (freq == 0) {
             // bucket spans several symbols: warp-cooperative forward search from s.  Lane i tests symbol s + i
             // (cdf[s+i] <= cf < cdf[s+i+1]); exactly one lane can hit, and a max-reduction broadcasts its
             // (freq, start) pair without a second round of dependent shared-memory loads.

@@ -131,7 +131,12 @@ __global__ void table_lut_kernel(BlobHeader hdr, unsigned char *__restrict__ blo
       // a bucket is "direct" (freq field != 0) only if it names ONE ORDINARY symbol; buckets that straddle a symbol
       // boundary, and buckets of the escape symbol (the last one), are left as "search from e.y" so that the
       // decoder's fast path needs a single test
-      if (next > cf1 && next > start && lo != nsym - 1) e.x = start | ((next - start) << 16);
+      if (next > cf1 && next > start) {
+        if (lo != nsym - 1)
+          e.x = start | ((next - start) << 16);
+        else
+          e.y = 0x80000000u | start;  // whole bucket inside the escape symbol: no search needed, freq = 2^16 - start
+      }
     }
     lut[b] = e;
   }
