@@ -226,10 +226,15 @@ def strings_to_device(strings: Sequence[bytes], device) -> tuple:
     begin = np.zeros(len(strings) + 1, dtype=np.int64)
     np.cumsum(lens, out=begin[1:])
     total = int(begin[-1])
-    host = torch.zeros(max(total, 1) * 4, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    host = torch.empty(max(total, 1) * 4, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
     hv = host.numpy()
-    for s, a in zip(strings, begin[:-1]):
-        hv[a * 4:a * 4 + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    for s, a, nwords in zip(strings, begin[:-1], lens):
+        n = len(s)
+        hv[a * 4:a * 4 + n] = np.frombuffer(s, dtype=np.uint8)
+        if n != nwords * 4:  # zero the padding of a string that is not a whole number of words
+            hv[a * 4 + n:(a + nwords) * 4] = 0
+    if total == 0:
+        hv[:] = 0
     words = host.view(torch.int32).to(device, non_blocking=True)
     wb = torch.from_numpy(begin).to(device, non_blocking=True)
     return words, wb, host
