@@ -281,16 +281,18 @@ def ours(args, rank, world):
     def _step_e2e(slot):
         torch.cuda.set_device(local)
         with torch.cuda.stream(e2e_streams[slot]), torch.no_grad():
-            xb = x_host.to(dev, non_blocking=True)
-            h2d = xb.numel() * 4
-            enc = net.compress(xb)
-            nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
-            d2h = nbytes
-            dec = net.decompress(enc["strings"], enc["shape"])
-            h2d += nbytes
-            out_hosts[slot].copy_(dec["x_hat"], non_blocking=True)
+            if args.e2e_device_io:   # caller moves the whole batch itself: x.to(device) / x_hat.cpu()
+                xb = x_host.to(dev, non_blocking=True)
+                enc = net.compress(xb)
+                dec = net.decompress(enc["strings"], enc["shape"])
+                out_hosts[slot].copy_(dec["x_hat"], non_blocking=True)
+            else:                    # host tensors straight into the API: micro-batches stream in and out
+                enc = net.compress(x_host)
+                dec = net.decompress(enc["strings"], enc["shape"], out=out_hosts[slot])
             torch.cuda.current_stream().synchronize()
-            d2h += out_hosts[slot].numel() * 4
+            nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
+            h2d = x_host.numel() * 4 + nbytes
+            d2h = nbytes + out_hosts[slot].numel() * 4
         return h2d, d2h, nbytes
 
     def run_e2e(n_steps):
@@ -530,6 +532,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-device-io", action="store_true",
+                    help="e2e: copy the whole batch to the device / back around the API calls instead of passing host tensors")
     ap.add_argument("--no-variants", action="store_true", help="skip the as-is / trained-rate variants of the workload")
     ap.add_argument("--gain-y", type=float, default=GAIN_Y, help="scale of the last g_a layer (stream rate, see GAIN_Y)")
     ap.add_argument("--gain-s", type=float, default=GAIN_S, help="scale of the last h_s layer")

@@ -224,6 +224,7 @@ class ScaleHyperprior(CompressionModel):
             # not queue behind whole analysis / synthesis grids of other requests in the block scheduler
             st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device, priority=int(__import__("os").environ.get("CAI_HYP_PRIO", "-1"))),
                   "syn": torch.cuda.Stream(device=device),
+                  "h2d": torch.cuda.Stream(device=device), "d2h": torch.cuda.Stream(device=device),
                   "pool": [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.coder_stream_pool)],
                   "next": 0}
             pool[str(device)] = st
@@ -255,19 +256,34 @@ class ScaleHyperprior(CompressionModel):
     def compress_to_device(self, x):
         """compress() with the strings left in HBM: per micro-batch ``coder.EncodedBatch`` lists."""
         self._check_tables()
-        _lib.require_cuda(x, "inputs")
+        host_in = not x.is_cuda
+        dev = self.gaussian_conditional._quantized_cdf.device if host_in else x.device
+        if host_in:
+            # host images (serving path): each micro-batch is copied in on a side stream while the previous one is
+            # being analysed; pinned memory makes the copies asynchronous.  The compute stays on the GPU.
+            _lib.require_cuda(self.gaussian_conditional._quantized_cdf, "model buffers")
+        else:
+            _lib.require_cuda(x, "inputs")
         eb_t, gc_t = self.entropy_bottleneck._table(), self.gaussian_conditional._table()
         starts = list(range(0, x.size(0), self.micro_batch))
-        S = self._streams(x.device, len(starts))
+        S = self._streams(dev, len(starts))
         coder_streams = self._take_coder_streams(S, len(starts))
         ana = S["ana"]
-        ana.wait_event(torch.cuda.current_stream(x.device).record_event())
-        x.record_stream(ana)
+        ana.wait_event(torch.cuda.current_stream(dev).record_event())
+        if not host_in:
+            x.record_stream(ana)
         y_encs, z_encs, shape = [], [], None
         for k, i in enumerate(starts):
             ck = coder_streams[k]
+            if host_in:
+                with torch.cuda.stream(S["h2d"]):
+                    xc = x[i:i + self.micro_batch].to(dev, non_blocking=True)
+                    ana.wait_event(S["h2d"].record_event())
+                    xc.record_stream(ana)
+            else:
+                xc = x[i:i + self.micro_batch]
             with torch.cuda.stream(ana):
-                y_sym, y_idx, z_sym, z_idx, shape = self._analysis_chunk(x[i:i + self.micro_batch])
+                y_sym, y_idx, z_sym, z_idx, shape = self._analysis_chunk(xc)
                 self._handoff(ck, y_sym, y_idx, z_sym, z_idx)
             with torch.cuda.stream(ck):
                 z_encs.append(coder.encode(eb_t, z_sym, z_idx))
@@ -284,7 +300,7 @@ class ScaleHyperprior(CompressionModel):
         return {"strings": [ys, zs], "shape": out["shape"]}
 
     @torch.no_grad()
-    def _decompress_chunks(self, chunks, shape, device, statuses=None):
+    def _decompress_chunks(self, chunks, shape, device, statuses=None, out=None):
         """chunks: list of (coder_stream, y_words, z_words, n) with *_words = (strings | None, device_words | None)."""
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         eb_t, gc_t = eb._table(), gc._table()
@@ -322,10 +338,24 @@ class ScaleHyperprior(CompressionModel):
         outs = []
         with torch.cuda.stream(syn):
             syn.wait_event(hyp.record_event())  # means_hat / shapes produced on "hyp"
+            row = 0
             for y_sym, means_hat, shp, done in pending:
                 syn.wait_event(done)
                 y_hat = kernels.dequantize(y_sym, means_hat, None, shp, _CL)
-                outs.append(self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True))
+                xc = self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True)
+                if out is None:
+                    outs.append(xc)
+                else:
+                    # host output buffer (serving path): this micro-batch goes home while the next one is synthesised
+                    d2h = S["d2h"]
+                    d2h.wait_event(syn.record_event())
+                    with torch.cuda.stream(d2h):
+                        out[row:row + xc.size(0)].copy_(xc, non_blocking=True)
+                    xc.record_stream(d2h)
+                    row += xc.size(0)
+        if out is not None:
+            main.wait_event(S["d2h"].record_event())
+            return {"x_hat": out}
         with torch.cuda.stream(syn):
             x_hat = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         main.wait_event(syn.record_event())
@@ -333,7 +363,9 @@ class ScaleHyperprior(CompressionModel):
         return {"x_hat": x_hat}
 
     @torch.no_grad()
-    def decompress(self, strings, shape):
+    def decompress(self, strings, shape, out=None):
+        """``out``: optional preallocated CPU tensor [B, 3, H, W] (pinned for asynchronous copies) that receives the
+        reconstruction micro-batch by micro-batch; the returned ``x_hat`` is then ``out`` itself."""
         assert isinstance(strings, list) and len(strings) == 2
         self._check_tables()
         if len(strings[0]) != len(strings[1]):
@@ -349,10 +381,12 @@ class ScaleHyperprior(CompressionModel):
             ys, zs = list(strings[0][i:i + self.micro_batch]), list(strings[1][i:i + self.micro_batch])
             chunks.append((coder_streams[k], (ys, None), (zs, None), len(ys)))
         statuses = []
-        out = self._decompress_chunks(chunks, shape, dev, statuses)
+        if out is not None and (out.is_cuda or out.dim() != 4 or out.size(0) != n or out.dtype != torch.float32):
+            raise ValueError("out must be a float32 CPU tensor [len(strings[0]), 3, H, W]")
+        res = self._decompress_chunks(chunks, shape, dev, statuses, out)
         torch.cuda.current_stream(dev).synchronize()  # one sync per call: surface decoder errors like the reference would
         coder.check_status(statuses)
-        return out
+        return res
 
     @torch.no_grad()
     def decompress_from_device(self, enc, shape):

@@ -137,3 +137,27 @@ def test_forward_shapes_and_training_step():
     aux.backward()
     grads = [p.grad for n, p in net.named_parameters()]
     assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+
+
+@pytest.mark.parametrize("name", ["hyperprior", "meanscale"])
+def test_host_tensor_io_matches_device_io(golden, name):
+    """Serving path: compress() accepts host images (streamed in micro-batch by micro-batch) and decompress(out=...)
+    streams the reconstruction into a host buffer; strings and pixels must be identical to the device-tensor path."""
+    net, g = _load(golden, name)
+    net.micro_batch = 1                       # several micro-batches -> the chunked copies are exercised
+    x = torch.from_numpy(g["x"]).float()
+    x = torch.cat([x, x.flip(0)], 0)
+    with torch.no_grad():
+        ref = net.compress(x.to(DEV))
+        for xin in (x.pin_memory(), x.clone()):
+            got = net.compress(xin)
+            assert got["strings"] == ref["strings"] and tuple(got["shape"]) == tuple(ref["shape"])
+        want = net.decompress(ref["strings"], ref["shape"])["x_hat"].cpu()
+        out = torch.empty_like(want).pin_memory()
+        res = net.decompress(ref["strings"], ref["shape"], out=out)
+        assert res["x_hat"] is out and torch.equal(out, want)
+        out2 = torch.zeros_like(want)         # pageable buffers work too (synchronous copies)
+        net.decompress(ref["strings"], ref["shape"], out=out2)
+        assert torch.equal(out2, want)
+        with pytest.raises(ValueError):
+            net.decompress(ref["strings"], ref["shape"], out=torch.empty(1, 3, 4, 4))
