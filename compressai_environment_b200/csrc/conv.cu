@@ -1141,11 +1141,7 @@ int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, in
   if (rc != CAI_OK) return rc;
   if (Cout == 3 && ksize == 5 && stride == 2 && pad == 2 && Ho == 2 * H && Wo == 2 * W && Npad % 4 == 0 && Npad >= 76 &&
       N <= 65535 && (reinterpret_cast<uintptr_t>(cols) & 15u) == 0 && !getenv("CAI_PATCH_GENERIC")) {
-    static bool attr_set = false;  // benign race: the attribute is idempotent
-    if (!attr_set) {
-      CAI_CUDA(cudaFuncSetAttribute(col2im_k5s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem));
-      attr_set = true;
-    }
+    CAI_CUDA(cudaFuncSetAttribute(col2im_k5s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem));
     dim3 tg((Wo + kC2iTX - 1) / kC2iTX, (Ho + kC2iTY - 1) / kC2iTY, N);
     col2im_k5s2_c3_kernel<<<tg, 256, kC2iSmem, static_cast<cudaStream_t>(stream_)>>>(
         cols, bias, H, W, Ho, Wo, Npad, out_layout, clamp_lo, clamp_hi, out);

@@ -13,6 +13,8 @@ Same constructor arguments, submodule names (``g_a``, ``g_s``, ``h_a``, ``h_s``,
 import math
 import warnings
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -209,7 +211,7 @@ class ScaleHyperprior(CompressionModel):
     # because nothing here synchronises the host, the analysis of the NEXT call overlaps this call's decode wait.
     max_streams = 8
 
-    coder_stream_pool = int(__import__("os").environ.get("CAI_CODER_STREAMS", "16"))
+    coder_stream_pool = int(os.environ.get("CAI_CODER_STREAMS", "16"))
 
     def _streams(self, device, n):
         """Shared, in-order transform streams -- "ana" (analysis), "hyp" (hyper-synthesis + index kernels: short work
@@ -222,7 +224,7 @@ class ScaleHyperprior(CompressionModel):
         if st is None:
             # "hyp" is high priority: its kernels are tiny and gate the start of the long y decodes, so they must
             # not queue behind whole analysis / synthesis grids of other requests in the block scheduler
-            st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device, priority=int(__import__("os").environ.get("CAI_HYP_PRIO", "-1"))),
+            st = {"ana": torch.cuda.Stream(device=device), "hyp": torch.cuda.Stream(device=device, priority=int(os.environ.get("CAI_HYP_PRIO", "-1"))),
                   "syn": torch.cuda.Stream(device=device),
                   "h2d": torch.cuda.Stream(device=device), "d2h": torch.cuda.Stream(device=device),
                   "pool": [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.coder_stream_pool)],
