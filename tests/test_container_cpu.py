@@ -1,0 +1,47 @@
+"""Container format against vectors written by the reference's own examples/codec.py
+(tests/golden/make_golden_container.py).  CPU only: the format is host-side byte handling."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_headers_match_reference(golden):
+    from compressai_environment_b200 import codec_io
+
+    g = golden("container")
+    for hb, name, metric, q in zip(g["header_bytes"], g["header_names"], g["header_metrics"], g["header_quality"]):
+        assert codec_io.pack_header(str(name), str(metric), int(q)) == hb.tobytes()
+        assert codec_io.unpack_header(hb.tobytes()) == (str(name), str(metric), int(q))
+    with pytest.raises(ValueError):
+        codec_io.pack_header("no-such-model", "mse", 1)
+    with pytest.raises(ValueError):
+        codec_io.unpack_header(bytes([200, 0]))
+
+
+def test_image_stream_is_byte_identical_and_round_trips(golden):
+    from compressai_environment_b200 import codec_io
+
+    g = golden("container")
+    strings = [[g["stream_y"].tobytes()], [g["stream_z"].tobytes()]]
+    buf = io.BytesIO()
+    n = codec_io.write_image(buf, "bmshj2018-hyperprior", "mse", 4, (501, 763), (8, 12), strings, bitdepth=8)
+    assert buf.getvalue() == g["stream"].tobytes() and n == len(g["stream"])
+    info = codec_io.read_image(io.BytesIO(g["stream"].tobytes()))   # a file the reference wrote
+    assert info["model"] == "bmshj2018-hyperprior" and info["metric"] == "mse" and info["quality"] == 4
+    assert info["original_size"] == (501, 763) and info["bitdepth"] == 8 and info["shape"] == (8, 12)
+    assert info["strings"] == strings
+    with pytest.raises(ValueError):
+        codec_io.read_image(io.BytesIO(g["stream"].tobytes()[:-3]))
+
+
+def test_pad_crop_geometry_matches_reference(golden):
+    from compressai_environment_b200 import codec_io
+
+    for h, w, H, W, y0, x0 in golden("container")["pad_geometry"].tolist():
+        x = torch.arange(h * w, dtype=torch.float32).reshape(1, 1, h, w) + 1.0
+        p = codec_io.pad(x, 64)
+        assert tuple(p.shape[2:]) == (H, W)
+        assert p[0, 0, y0, x0] == 1.0 and int(torch.count_nonzero(p)) == h * w
+        assert torch.equal(codec_io.crop(p, (h, w)), x)

@@ -161,3 +161,24 @@ def test_host_tensor_io_matches_device_io(golden, name):
         assert torch.equal(out2, want)
         with pytest.raises(ValueError):
             net.decompress(ref["strings"], ref["shape"], out=torch.empty(1, 3, 4, 4))
+
+
+def test_container_encode_decode_image(golden):
+    """examples/codec.py encode_image / decode_image flow on the GPU path: odd-sized image -> centre pad to 64 ->
+    compress -> container bytes -> parse -> decompress -> crop; equals compress/decompress of the padded tensor."""
+    import io
+    from compressai_environment_b200 import codec_io
+
+    net, g = _load(golden, "hyperprior")
+    x = torch.from_numpy(g["x"]).float()[:1, :, :61, :100].contiguous().to(DEV)
+    buf = io.BytesIO()
+    res = codec_io.encode_image(net, x, buf, "bmshj2018-hyperprior", "mse", 4)
+    assert abs(res["bpp"] - len(buf.getvalue()) * 8 / (61 * 100)) < 1e-12
+    info = codec_io.decode_image(net, io.BytesIO(buf.getvalue()))
+    assert info["model"] == "bmshj2018-hyperprior" and info["quality"] == 4 and info["original_size"] == (61, 100)
+    assert tuple(info["x_hat"].shape) == (1, 3, 61, 100)
+    with torch.no_grad():
+        xp = codec_io.pad(x, 64)
+        enc = net.compress(xp)
+        want = codec_io.crop(net.decompress(enc["strings"], enc["shape"])["x_hat"], (61, 100))
+    assert info["strings"] == enc["strings"] and torch.equal(info["x_hat"], want)
