@@ -45,3 +45,17 @@ def test_pad_crop_geometry_matches_reference(golden):
         assert tuple(p.shape[2:]) == (H, W)
         assert p[0, 0, y0, x0] == 1.0 and int(torch.count_nonzero(p)) == h * w
         assert torch.equal(codec_io.crop(p, (h, w)), x)
+
+
+def test_ms_ssim_restatement_sanity():
+    from compressai_environment_b200.utils.eval_model import ms_ssim, psnr
+
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 176, 200)
+    assert abs(float(ms_ssim(x, x)) - 1.0) < 1e-6
+    a = float(ms_ssim(x, (x + 0.05 * torch.randn_like(x)).clamp(0, 1)))
+    b = float(ms_ssim(x, (x + 0.20 * torch.randn_like(x)).clamp(0, 1)))
+    assert 0.0 < b < a < 1.0
+    assert abs(psnr(x, x + 0.1) - 20.0) < 1e-3
+    with pytest.raises(ValueError):
+        ms_ssim(x[..., :100, :100], x[..., :100, :100])

@@ -182,3 +182,25 @@ def test_container_encode_decode_image(golden):
         enc = net.compress(xp)
         want = codec_io.crop(net.decompress(enc["strings"], enc["shape"])["x_hat"], (61, 100))
     assert info["strings"] == enc["strings"] and torch.equal(info["x_hat"], want)
+
+
+def test_eval_model_protocol_matches_reference(golden):
+    """compressai.utils.eval_model inference / inference_entropy_estimation on the GPU path vs the numbers the
+    reference's own functions produced for the same seeded model and image (tests/golden/make_golden_eval.py)."""
+    from compressai_environment_b200.utils import eval_model as em
+
+    net, g = _load(golden, "hyperprior")
+    e = golden("eval")
+    x = torch.from_numpy(g["x"]).float().to(DEV)
+    h, w = [int(v) for v in e["crop"]]
+    rv = em.inference(net, x[0, :, :h, :w].contiguous())
+    assert rv["bpp"] == float(e["inf_bpp"])                       # same strings -> same size
+    assert abs(rv["psnr"] - float(e["inf_psnr"])) <= 0.02         # reconstructions agree to ~2e-3
+    assert rv["encoding_time"] > 0 and rv["decoding_time"] > 0 and "ms-ssim" not in rv   # 61x100 is below 160
+    est = em.inference_entropy_estimation(net, x[0])
+    assert abs(est["bpp"] - float(e["est_bpp"])) <= 2e-3 * float(e["est_bpp"])
+    assert abs(est["psnr"] - float(e["est_psnr"])) <= 0.02
+    avg = em.eval_model(net, [x[0], x[1]])
+    assert set(avg) >= {"psnr", "bpp", "encoding_time", "decoding_time"}
+    with pytest.raises(ValueError):
+        em.eval_model(net, [x[0]], half=True)
