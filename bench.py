@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=32)
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-sample", type=int, default=48, help="images in the cpu_baseline sample (~10 s of host work)")
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -539,7 +539,7 @@ def main():
     ap.add_argument("--gain-y", type=float, default=GAIN_Y, help="scale of the last g_a layer (stream rate, see GAIN_Y)")
     ap.add_argument("--gain-s", type=float, default=GAIN_S, help="scale of the last h_s layer")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (user streams) in the device-timed loop")
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="requests in flight (host threads) in the e2e loop")
+    ap.add_argument("--e2e-inflight", type=int, default=5, help="requests in flight (host threads) in the e2e loop")
     args = ap.parse_args()
     globals().update(GAIN_Y=args.gain_y, GAIN_S=args.gain_s)
     rank = int(os.environ.get("RANK", 0))
