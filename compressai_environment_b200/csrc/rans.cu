@@ -486,32 +486,46 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
             // bypass / escape decoding (rans_interface.cpp:256-278).  Count nibble(s) one at a time, then the
             // payload nibbles in groups: with L = bitlen(x), the reference refills after pop number
             // ceil((L - 31) / 4) (that pop leaves x < 2^31), so that many nibbles can be taken at once.
-            uint32_t t = static_cast<uint32_t>(x) & 15u;
-            x >>= 4;
-            if (x < (1ull << 31)) x = (x << 32) | wf.take();
-            int32_t nb = static_cast<int32_t>(t);
-            while (t == 15u) {
-              t = static_cast<uint32_t>(x) & 15u;
-              x >>= 4;
-              if (x < (1ull << 31)) x = (x << 32) | wf.take();
-              nb += static_cast<int32_t>(t);
+            // Common case first: the count nibble t0 (< 15) and its t0 payload nibbles can all be popped before the
+            // reference would refill (pop number js0 = ceil((L - 31) / 4) is the one that leaves x < 2^31), so they
+            // come off in one shift, followed by at most one refill.  Anything else takes the general loop.
+            uint32_t raw;
+            {
+              const uint32_t t0 = static_cast<uint32_t>(x) & 15u;
+              const int js0 = (64 - __clzll(x) - 28) >> 2;
+              if (t0 < 15u && static_cast<int>(t0) + 1 <= js0) {
+                raw = static_cast<uint32_t>((x >> 4) & ((1ull << (4u * t0)) - 1ull));
+                x >>= 4u * (t0 + 1u);
+                if (static_cast<int>(t0) + 1 == js0) x = (x << 32) | wf.take();
+              } else {
+                uint32_t t = static_cast<uint32_t>(x) & 15u;
+                x >>= 4;
+                if (x < (1ull << 31)) x = (x << 32) | wf.take();
+                int32_t nb = static_cast<int32_t>(t);
+                while (t == 15u) {
+                  t = static_cast<uint32_t>(x) & 15u;
+                  x >>= 4;
+                  if (x < (1ull << 31)) x = (x << 32) | wf.take();
+                  nb += static_cast<int32_t>(t);
+                }
+                uint64_t acc = 0;
+                int done = 0;
+                int rem = nb;
+                while (rem > 0) {
+                  const int L = 64 - __clzll(x);
+                  int js = (L - 31 + 3) >> 2;
+                  if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
+                  const int c = rem < js ? rem : js;
+                  const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
+                  x >>= 4 * c;
+                  if (done < 8) acc |= bits << (4 * done);
+                  done += c;
+                  rem -= c;
+                  if (c == js) x = (x << 32) | wf.take();
+                }
+                raw = static_cast<uint32_t>(acc);
+              }
             }
-            uint64_t acc = 0;
-            int done = 0;
-            int rem = nb;
-            while (rem > 0) {
-              const int L = 64 - __clzll(x);
-              int js = (L - 31 + 3) >> 2;
-              if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
-              const int c = rem < js ? rem : js;
-              const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
-              x >>= 4 * c;
-              if (done < 8) acc |= bits << (4 * done);
-              done += c;
-              rem -= c;
-              if (c == js) x = (x << 32) | wf.take();
-            }
-            const uint32_t raw = static_cast<uint32_t>(acc);
             const int32_t sraw = static_cast<int32_t>(raw);
             v = sraw >> 1;
             v = (sraw & 1) ? (-v - 1) : (v + maxv);
