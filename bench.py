@@ -470,6 +470,7 @@ def ours(args, rank, world):
                            "frac": iso["index"]["gbs"] / hbm, "traffic": None, "avg_launch_ms": iso["index"]["ms"],
                            "alg_bytes_per_launch": iso["index"]["alg_bytes"],
                            "how": "timed alone, L2 flushed, median of 5"} if iso else None,
+        "rans_c3": iso["c3"] if iso else None,
         "variants": variants,
         "cpu_baseline": cpu,
     }
@@ -518,6 +519,29 @@ def isolated_kernels(model, mb, B, dev):
             _lib.ptr(y), _lib.ptr(sc), None, _lib.ptr(tab), int(tab.numel()), 0.11, CAI_LAYOUT_NHWC, B, M_CH,
             (H // 16) * (W // 16), _lib.ptr(sym), _lib.ptr(idx), _lib.current_stream()), "cai_gc_quantize_index"))
         out["index"] = {"ms": ms, "gbs": 16 * n / ms / 1e6, "alg_bytes": 16 * n}
+        del y, sc, sym, idx
+        # C3 (BASELINE.json configs[2]): raw coder, 2^28 symbols = 4096 strings x 65,536, the model's 64-row Gaussian
+        # table, symbols ~ round(N(0, 1) * scale_table[idx]) (4.6 bit/symbol, no escapes); decoded symbols checked
+        from compressai_environment_b200 import coder
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        gc = model.gaussian_conditional
+        Bs, ns = 4096, 65536
+        cidx = torch.randint(0, int(tab.numel()), (Bs, ns), generator=gen, device=dev, dtype=torch.int32)
+        csym = torch.round(torch.randn((Bs, ns), generator=gen, device=dev) * tab[cidx.long()]).to(torch.int32)
+        table = gc._table()
+        enc = coder.encode(table, csym, cidx)
+        words = enc.device_words()
+        dec = coder.decode(table, None, cidx, device_words=words)
+        ok = bool(torch.equal(dec, csym))
+        del dec
+        e_ms = timed(lambda: coder.encode(table, csym, cidx), 3)
+        d_ms = timed(lambda: coder.decode(table, None, cidx, device_words=words), 3)
+        payload = int(enc.n_words.sum().item()) * 4
+        out["c3"] = {"workload": "C3 raw coder: 4096 strings x 65,536 symbols, 64-row Gaussian table",
+                     "encode_msym_s": Bs * ns / e_ms / 1e3, "decode_msym_s": Bs * ns / d_ms / 1e3,
+                     "encode_ms": e_ms, "decode_ms": d_ms, "bits_per_symbol": payload * 8 / (Bs * ns),
+                     "encode_alg_gbs": (8 * Bs * ns + payload) / e_ms / 1e6,
+                     "decode_alg_gbs": (8 * Bs * ns + payload) / d_ms / 1e6, "round_trip_exact": ok}
     return out
 
 
