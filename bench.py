@@ -176,6 +176,21 @@ def cpu_baseline_sample(n_images):
             "sample": f"{n_images} images in batches of 8, compress+decompress ({dt:.1f} s), all host threads"}, enc
 
 
+def interval_union(intervals):
+    """Total length covered by a list of (start, end) intervals (any order, may overlap)."""
+    total, cur_a, cur_b = 0.0, None, None
+    for a, b in sorted(intervals):
+        if cur_b is None or a > cur_b:
+            if cur_b is not None:
+                total += cur_b - cur_a
+            cur_a, cur_b = a, b
+        else:
+            cur_b = max(cur_b, b)
+    if cur_b is not None:
+        total += cur_b - cur_a
+    return total
+
+
 def max_over_ranks(values, device, world):
     """Job time = the slowest rank's time (every rank processes its own shard; no data-path collective)."""
     import torch
@@ -325,9 +340,9 @@ def ours(args, rank, world):
         transforms.TIMING = {}
         launches0 = _lib.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # two requests in flight, as a serving loop would run them: consecutive steps are issued on alternating
+        # --inflight requests in flight, as a serving loop would run them: consecutive steps are issued on alternating
         # user streams so that step i+1's analysis overlaps step i's decode latency; every step still does all
-        # of its work, and the timed region ends only when both streams have drained.
+        # of its work, and the timed region ends only when all user streams have drained.
         users = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.inflight))] if args.inflight > 1 else []
         e0.record()
         for u in users:
@@ -369,16 +384,7 @@ def ours(args, rank, world):
         # launches of different requests overlap (analysis of step i+1 runs beside the synthesis of step i and share
         # the SMs), which inflates every individual duration; the time during which AT LEAST ONE conv_gemm launch is
         # executing (union of the event intervals) is the kernel's real occupancy of the timed region
-        conv_union, cur_a, cur_b = 0.0, None, None
-        for a, b in conv_iv:
-            if cur_b is None or a > cur_b:
-                if cur_b is not None:
-                    conv_union += cur_b - cur_a
-                cur_a, cur_b = a, b
-            else:
-                cur_b = max(cur_b, b)
-        if cur_b is not None:
-            conv_union += cur_b - cur_a
+        conv_union = interval_union(conv_iv)
         conv_union_step = conv_union / args.steps if conv_ms else None
         # algorithmic FLOPs (2 * MAC): compress g_a + h_a + h_s = 35.31 GFLOP,
         # decompress h_s + g_s = 34.24 GFLOP per 768x512 image

@@ -3,6 +3,7 @@ ctypes table in _lib.py covers exactly that set.  No compute calls (there is no 
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 
@@ -59,3 +60,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_conv_desc_layout_matches_header(tmp_path):
+    """The ctypes mirror of cai_conv_desc must have the C compiler's size and field offsets."""
+    import ctypes, subprocess
+
+    from compressai_environment_b200._lib import ConvDesc
+
+    fields = ["a_hi", "bias", "out_f32", "abs_lo", "N", "Cout", "is", "ntaps", "BN", "epilogue", "clamp_lo", "dy", "dx",
+              "glen", "gdn_w", "gdn_beta", "gdn_mode"]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cai_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(cai_conv_desc));\n'
+                   + "".join(f'  printf(" %zu", offsetof(cai_conv_desc, {f}));\n' for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got[0] == ctypes.sizeof(ConvDesc)
+    for f, off in zip(fields, got[1:]):
+        assert getattr(ConvDesc, "is_" if f == "is" else f).offset == off, f
+
+
+def test_interval_union():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.interval_union([]) == 0.0
+    assert bench.interval_union([(0, 1), (2, 3)]) == 2.0
+    assert bench.interval_union([(2, 5), (0, 3), (4, 4.5), (10, 11)]) == 6.0
