@@ -59,3 +59,25 @@ def test_ms_ssim_restatement_sanity():
     assert abs(psnr(x, x + 0.1) - 20.0) < 1e-3
     with pytest.raises(ValueError):
         ms_ssim(x[..., :100, :100], x[..., :100, :100])
+
+
+def test_container_round_trip_random_strings():
+    """Property: any (model, metric, quality, size, shape, strings) survives write_image -> read_image."""
+    import random
+
+    from compressai_environment_b200 import codec_io
+
+    rnd = random.Random(11)
+    for _ in range(50):
+        model = rnd.choice(sorted(codec_io.MODEL_IDS))
+        metric = rnd.choice(sorted(codec_io.METRIC_IDS))
+        q = rnd.randint(1, 8)
+        size = (rnd.randint(1, 5000), rnd.randint(1, 5000))
+        shape = (rnd.randint(1, 300), rnd.randint(1, 300))
+        strings = [[bytes(rnd.getrandbits(8) for _ in range(rnd.choice([0, 8, 12, 4096])))] for _ in range(rnd.randint(1, 3))]
+        buf = io.BytesIO()
+        n = codec_io.write_image(buf, model, metric, q, size, shape, strings, bitdepth=rnd.choice([8, 10]))
+        assert n == len(buf.getvalue()) == 2 + 8 + 1 + 12 + sum(4 + len(s[0]) for s in strings)
+        info = codec_io.read_image(io.BytesIO(buf.getvalue()))
+        assert (info["model"], info["metric"], info["quality"]) == (model, metric, q)
+        assert info["original_size"] == size and info["shape"] == shape and info["strings"] == strings
