@@ -20,10 +20,17 @@
 // for padding) straight into the UMMA canonical K-major layout; weights are pre-packed on the host in
 // that same layout and arrive with one TMA bulk copy per stage.
 //
-// CTA = 5 warps: warps 0-3 produce the A tile (thread = pixel row) and later run the epilogue (thread =
-// TMEM lane), warp 4 issues the MMAs (one elected lane) and owns the TMEM allocation.  smem ring of
-// kStages (A hi/lo 32 KB + B hi/lo BN*256 B per stage), mbarrier full/empty per stage, accumulator
-// 128 lanes x BN columns of TMEM, drained with tcgen05.ld.32x32b.x16.
+// CTA = 5 warps, two CTAs per SM: warps 0-1 produce the A tile (4 lanes per pixel), warps 0-3 run the epilogue
+// (thread = TMEM lane = pixel row), warp 4 issues the MMAs (one elected lane) and owns the TMEM allocation.  smem
+// ring of 2-3 stages of BK = 32 (A hi/lo 2 x 8.3 KB + B hi/lo BN*128 B per stage), mbarrier full/empty per stage
+// (producers arrive asynchronously with cp.async.mbarrier.arrive.noinc), accumulators of 128 lanes x BN columns of
+// TMEM (main + GDN norm), drained with double-buffered tcgen05.ld.
+//
+// k-step order.  Taps come in groups (same dy, dx congruent modulo the input stride) whose input pixel sets are
+// one-pixel shifts of each other; the kernel walks  group -> channel chunk -> tap in group  and the A copies are
+// L1-allocating (cp.async.ca), so only the first tap of a group fetches its activation lines from L2 and the others
+// hit L1.  This halves the L2 -> SM traffic of the 5x5 layers and was worth 2.85 -> 2.08 ms on the largest launch
+// (an ablation had shown the A-operand path, not the tensor pipe or the weights, to be the bound).
 #include <cuda_bf16.h>
 
 #include <cstdlib>
