@@ -8,8 +8,9 @@
 //
 // Layout: inputs are logical (N, C, HW) latents stored NCHW or NHWC (channels-last, what the conv
 // kernels produce); integer outputs are always in coder order (N, C, HW) so that string b is a
-// contiguous run.  The NHWC variants transpose 32x32 tiles through shared memory so that both the
-// loads (along C) and the stores (along HW) are full 128-byte lines.
+// contiguous run.  The NHWC variants transpose tiles through shared memory so that both the
+// loads (along C) and the stores (along HW) are full 128-byte lines (measured: 3.5-4.0 TB/s, 53-61 % of the
+// 6.55 TB/s copy peak; the pure elementwise NCHW variant 4.4-5.3 TB/s).
 //
 // Algorithmic bytes per element: GC 16 B (20 B with means), EB 12 B, dequantize 8-12 B.
 #include "common.cuh"
