@@ -45,6 +45,29 @@ struct DeviceProps {
 // Cached per-thread view of the current device (cudaGetDevice + attributes).
 int get_device_props(DeviceProps *out);
 
+// Opt `kernel` into the device's full dynamic shared memory (opt-in maximum minus the kernel's static shared memory)
+// ONCE per (device, kernel), under a mutex.  cudaFuncAttributeMaxDynamicSharedMemorySize is per-function state
+// shared by all host threads: setting it to each launch's own size let a concurrent caller LOWER it between another
+// thread's set and launch ("invalid argument").  It is never lowered here, so the entry points are re-entrant.
+// `max_dynamic` (optional) receives the limit that was set.  `carveout` >= 0 additionally sets the preferred
+// shared-memory carve-out (percent), also once.
+int optin_max_smem(const void *kernel, const DeviceProps &dp, int *max_dynamic = nullptr, int carveout = -1);
+
+// Experiment knobs (environment), read ONCE at first use -- never per launch.
+struct Knobs {
+  int conv_stages = 0;      // CAI_CONV_STAGES   (0 = automatic)
+  int conv_generic = 0;     // CAI_CONV_GENERIC  (force the all-runtime-flags instantiation)
+  int conv_carveout = -1;   // CAI_CONV_CARVEOUT (percent, -1 = driver default)
+  int conv_debug = 0;       // CAI_CONV_DEBUG    (only honoured by -DCAI_DEBUG_BUILD builds)
+  int patch_generic = 0;    // CAI_PATCH_GENERIC (generic im2col / col2im kernels)
+  int coder_warps = 0;      // CAI_CODER_WARPS   (0 = automatic)
+  int lut_buckets = 0;      // CAI_LUT_BUCKETS   (0 = automatic)
+  int table_smem_kb = -1;   // CAI_TABLE_SMEM_KB (-1 = no cap)
+  int conv_persist = -1;    // CAI_CONV_PERSIST  (-1 = automatic)
+  int coder_lut_adapt = -1; // CAI_LUT_ADAPT     (-1 = automatic)
+};
+const Knobs &knobs();
+
 // ---- packed CDF table blob (see table.cu) ----------------------------------------------------------
 constexpr uint32_t kBlobMagic = 0x43414931u;  // "CAI1"
 

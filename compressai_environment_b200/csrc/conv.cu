@@ -51,7 +51,14 @@ constexpr int kMaxTaps = 32;
 constexpr uint32_t kLboA = kBM * 16u + 32u;
 constexpr uint32_t kSpinLimit = 1u << 28;
 
-__device__ long long g_conv_trace[64 * 8];  // experiment: phase timestamps of the first 64 CTAs (debug bit 32)
+// Ablation / trace instrumentation exists only in -DCAI_DEBUG_BUILD builds (`make DEBUG=1`); release kernels carry
+// none of it: CAI_DBG() folds to false and CAI_TRACE() to nothing at compile time.
+#ifdef CAI_DEBUG_BUILD
+__device__ long long g_conv_trace[64 * 8];  // phase timestamps of the first 64 CTAs (debug bit 32)
+#define CAI_DBG(mask) ((p.debug & (mask)) != 0)
+#else
+#define CAI_DBG(mask) (false)
+#endif
 
 struct ConvKernelParams {
   const __nv_bfloat16 *a_hi, *a_lo;  // [N, H, W, Cin] bf16 planes
@@ -199,7 +206,11 @@ __device__ __forceinline__ Pack8 split8(const float *v) {
   return p;
 }
 
-#define CAI_TRACE(slot) do { if ((p.debug & 32) && blockIdx.x < 64 && blockIdx.y == 0 && tid == 0) g_conv_trace[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+#ifdef CAI_DEBUG_BUILD
+#define CAI_TRACE(slot) do { if (CAI_DBG(32) && blockIdx.x < 64 && blockIdx.y == 0 && tid == 0) g_conv_trace[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+#else
+#define CAI_TRACE(slot) do { } while (0)
+#endif
 
 // KIND selects a specialised epilogue so that each instantiation stays small (the all-runtime-flags version is 33k
 // SASS instructions and thrashes the instruction cache in its epilogue loops):
@@ -352,7 +363,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       const int64_t koff = static_cast<int64_t>(dx) * p.Cin + kbase;
 #pragma unroll
       for (int it = 0; it < kLoadIters; ++it) {
-        if (p.debug & 1) break;
+        if CAI_DBG(1) break;
         const bool x_ok = static_cast<uint32_t>(ld_ix[it] + dx) < static_cast<uint32_t>(p.W);
         const uint32_t nbytes = (k_ok && x_ok) ? tap_bytes[it] : 0u;
         const int64_t off = nbytes ? tap_off[it] + koff : 0;
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         cp_async16(sa + a_plane + ld_so[it], p.a_lo + off, nbytes);
       }
       if (tid == 0) {
-        if (p.debug & 2) {
+        if CAI_DBG(2) {
           mbar_arrive(&full_bar[s]);
         } else {
           mbar_expect_tx(&full_bar[s], 2 * b_plane);
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
       // The TMEM load of slab g+1 is in flight while slab g is processed (two register buffers).
       uint32_t rawbuf[2][32];
-      if (!(p.debug & 128)) tmem_ld32_nowait(tmem_base + lane_base, rawbuf[0]);
+      if (!CAI_DBG(128)) tmem_ld32_nowait(tmem_base + lane_base, rawbuf[0]);
 #pragma unroll
       for (int g = 0; g < kMaxGdnK; ++g) {
         if (g >= gdn_ksteps) break;
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         const int col0 = g * kBK;
         const bool any = col0 < BN;  // warp-uniform (BN is a multiple of 16: a k-step may be half empty)
         tmem_wait_ld();
-        if (g + 1 < gdn_ksteps && col0 + kBK < BN && !(p.debug & 128))
+        if (g + 1 < gdn_ksteps && col0 + kBK < BN && !CAI_DBG(128))
           tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0 + kBK), rawbuf[(g + 1) & 1]);
 #pragma unroll
         for (int c = 0; c < kBK / 8; ++c) {
@@ -475,7 +486,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           *reinterpret_cast<uint4 *>(sa + so) = vh;
           *reinterpret_cast<uint4 *>(sa + a_plane + so) = vl;
         }
-        if (!(p.debug & 64)) fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!CAI_DBG(64)) fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(&gfull_bar[g]);   // every writer arrives: no CTA-wide barrier needed
       }
       CAI_TRACE(4);
@@ -536,7 +547,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         if (fuse_gdn) tmem_ld16_nowait(tmem_base + lane_base + acc_cols + static_cast<uint32_t>(c0), raw2);
       };
       auto process = [&](int c0, const uint32_t (&raw)[16], const uint32_t (&raw2)[16]) {
-        if (!row_ok || (p.debug & 8)) return;
+        if (!row_ok || CAI_DBG(8)) return;
         const int cg = n0 + c0;  // global output channel of raw[0]
         if (cg >= p.Cout) return;
         float v[16];
@@ -652,7 +663,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       if (cA == 0) CAI_TRACE(6);
       // ---- phase 2: cooperative copy-out, 16-byte units, consecutive lanes along a row
       const int cols_here = (cB - cA < p.Cout - (n0 + cA)) ? (cB - cA) : (p.Cout - (n0 + cA));
-      if (cols_here > 0 && !(p.debug & 8)) {
+      if (cols_here > 0 && !CAI_DBG(8)) {
 #pragma unroll 1
         for (int bi = 0; bi < nbuf; ++bi) {
           const StageBuf sb = bufs[bi];
@@ -706,7 +717,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         const uint32_t a_hi = sa, a_lo = sa + a_plane, b_hi = sa + 2 * a_plane, b_lo = b_hi + b_plane;
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {
-          if (p.debug & 4) break;
+          if CAI_DBG(4) break;
           const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, 128);
           const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, 128);
           const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, 128);
@@ -1045,10 +1056,10 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   // 128->128 k5 s2 layer: 2.19 ms with 3 stages, 2.08 ms with 2).
   if (d->ntaps > 1 && stages > 2) stages = 2;
   if (stages < 2) stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes) >= 2 ? 2 : stages;
-  if (const char *ov = getenv("CAI_CONV_STAGES")) {  // tuning override (experiments only)
-    const int v = atoi(ov);
+  const Knobs &kn = knobs();
+  if (kn.conv_stages >= 2) {  // tuning override (experiments only)
     const int cap = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes);
-    if (v >= 2) stages = v < cap ? v : cap;
+    stages = kn.conv_stages < cap ? kn.conv_stages : cap;
     if (stages > 4) stages = 4;
   }
   const int ksteps = p.ntaps * p.kchunks;
@@ -1058,7 +1069,9 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   p.gdn_w = static_cast<const unsigned char *>(d->gdn_w);
   p.gdn_beta = d->gdn_beta;
   p.gdn_mode = d->gdn_mode;
-  if (const char *dbg = getenv("CAI_CONV_DEBUG")) p.debug = atoi(dbg);
+#ifdef CAI_DEBUG_BUILD
+  p.debug = kn.conv_debug;
+#endif
   if (p.gdn_w) {
     CAI_CHECK_ARG(d->BN == d->Cout && d->BN <= 256, "cai_conv_gemm: fused GDN needs all channels in one tile (Cout <= 256)");
     CAI_CHECK_ARG(d->gdn_beta && (d->gdn_mode == 1 || d->gdn_mode == 2), "cai_conv_gemm: fused GDN needs beta and mode 1|2");
@@ -1077,18 +1090,15 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   if (p.gdn_w && only_planes && no_clamp) kind = 1;
   else if (!p.gdn_w && d->epilogue <= 2 && only_planes && no_clamp) kind = 2;
   else if (!p.gdn_w && d->epilogue <= 2 && d->out_f32 && !d->out_hi && !d->sq_hi) kind = 3;
-  if (getenv("CAI_CONV_GENERIC")) kind = 0;
+  if (kn.conv_generic) kind = 0;
   const dim3 grid(static_cast<unsigned>(mt), static_cast<unsigned>(nt));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  int carveout = -1;  // CAI_CONV_CARVEOUT: preferred shared-memory carve-out in percent (experiments only)
-  if (const char *ov = getenv("CAI_CONV_CARVEOUT")) carveout = atoi(ov);
-#define CAI_LAUNCH_KIND(K)                                                                                           \
-  do {                                                                                                               \
-    CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                                  static_cast<int>(smem)));                                                          \
-    if (carveout >= 0)                                                                                               \
-      CAI_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout)); \
-    conv_gemm_kernel<K><<<grid, kConvThreads, smem, st>>>(p);                                                       \
+  // the kernel's dynamic shared memory limit (and the optional carve-out knob) is set once per device, never per launch
+#define CAI_LAUNCH_KIND(K)                                                                                       \
+  do {                                                                                                           \
+    rc = optin_max_smem(reinterpret_cast<const void *>(conv_gemm_kernel<K>), dp, nullptr, kn.conv_carveout);     \
+    if (rc != CAI_OK) return rc;                                                                                 \
+    conv_gemm_kernel<K><<<grid, kConvThreads, smem, st>>>(p);                                                   \
   } while (0)
   switch (kind) {
     case 1: CAI_LAUNCH_KIND(1); break;
@@ -1101,10 +1111,13 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   return CAI_OK;
 }
 
-__attribute__((visibility("default"))) int cai_debug_conv_trace(long long *out_host) {  // experiment helper (not part of the documented ABI surface)
+#ifdef CAI_DEBUG_BUILD
+// experiment helper of debug builds only (tools/conv_probe.py); not part of the ABI in include/cai_b200.h
+__attribute__((visibility("default"))) int cai_debug_conv_trace(long long *out_host) {
   CAI_CUDA(cudaMemcpyFromSymbol(out_host, g_conv_trace, sizeof(long long) * 64 * 8));
   return CAI_OK;
 }
+#endif
 
 int cai_split_planes(const float *x, int32_t layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad, void *hi, void *lo,
                      cai_stream_t stream_) {
@@ -1128,7 +1141,7 @@ int cai_im2col_split(const float *x, int32_t layout, int32_t N, int32_t C, int32
   const int grid = ew_grid2(dp, static_cast<int64_t>(N) * Ho * Wo * (Kpad / 8));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   __nv_bfloat16 *h = static_cast<__nv_bfloat16 *>(hi), *l = static_cast<__nv_bfloat16 *>(lo);
-  if (C == 3 && ksize == 5 && stride == 2 && pad == 2 && Kpad >= 75 && N <= 65535 && !getenv("CAI_PATCH_GENERIC")) {
+  if (C == 3 && ksize == 5 && stride == 2 && pad == 2 && Kpad >= 75 && N <= 65535 && !knobs().patch_generic) {
     dim3 tg((Wo + kI2cTX - 1) / kI2cTX, (Ho + kI2cTY - 1) / kI2cTY, N);
     im2col_k5s2_c3_kernel<<<tg, 256, 0, st>>>(x, layout, H, W, Ho, Wo, Kpad, h, l);
   } else if (C == 3 && ksize == 5)
@@ -1147,8 +1160,9 @@ int cai_col2im(const float *cols, const float *bias, int32_t N, int32_t Cout, in
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
   if (Cout == 3 && ksize == 5 && stride == 2 && pad == 2 && Ho == 2 * H && Wo == 2 * W && Npad % 4 == 0 && Npad >= 76 &&
-      N <= 65535 && (reinterpret_cast<uintptr_t>(cols) & 15u) == 0 && !getenv("CAI_PATCH_GENERIC")) {
-    CAI_CUDA(cudaFuncSetAttribute(col2im_k5s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2iSmem));
+      N <= 65535 && (reinterpret_cast<uintptr_t>(cols) & 15u) == 0 && !knobs().patch_generic) {
+    rc = optin_max_smem(reinterpret_cast<const void *>(col2im_k5s2_c3_kernel), dp);
+    if (rc != CAI_OK) return rc;
     dim3 tg((Wo + kC2iTX - 1) / kC2iTX, (Ho + kC2iTY - 1) / kC2iTY, N);
     col2im_k5s2_c3_kernel<<<tg, 256, kC2iSmem, static_cast<cudaStream_t>(stream_)>>>(
         cols, bias, H, W, Ho, Wo, Npad, out_layout, clamp_lo, clamp_hi, out);

@@ -396,15 +396,18 @@ int cai_eb_forward(const float *x, const float *tparams, const int32_t *filters_
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
   const size_t smem = sizeof(float) * static_cast<size_t>(C) * sp.stride;
-  CAI_CHECK_ARG(smem <= static_cast<size_t>(dp.max_smem_optin), "cai_eb_forward: too many channels (%lld)",
-                static_cast<long long>(C));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = ew_grid(dp, n, 256);
+  const void *fn = (maxf <= 3) ? reinterpret_cast<const void *>(eb_forward_kernel<3>)
+                               : reinterpret_cast<const void *>(eb_forward_kernel<8>);
+  int max_dyn = 0;
+  rc = optin_max_smem(fn, dp, &max_dyn);  // once per device; never per launch (host threads share the attribute)
+  if (rc != CAI_OK) return rc;
+  CAI_CHECK_ARG(smem <= static_cast<size_t>(max_dyn), "cai_eb_forward: too many channels (%lld)",
+                static_cast<long long>(C));
   if (maxf <= 3) {
-    CAI_CUDA(cudaFuncSetAttribute(eb_forward_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     eb_forward_kernel<3><<<grid, 256, smem, stream>>>(x, tparams, medians, noise, sp, mode, bound_lik, layout, C, HW, n, out, lik);
   } else {
-    CAI_CUDA(cudaFuncSetAttribute(eb_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     eb_forward_kernel<8><<<grid, 256, smem, stream>>>(x, tparams, medians, noise, sp, mode, bound_lik, layout, C, HW, n, out, lik);
   }
   CAI_LAUNCH_CHECK();

@@ -212,8 +212,13 @@ extern "C" int cai_pmf_to_quantized_cdf(const float *pmf, const int32_t *pmf_len
   int P = 2;
   while (P < Lp + 1) P <<= 1;
   const size_t smem = static_cast<size_t>(P) * (sizeof(unsigned long long) + 2 * sizeof(uint32_t));
-  CAI_CUDA(cudaFuncSetAttribute(pmf_to_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  int max_dyn = 0;
+  rc = optin_max_smem(reinterpret_cast<const void *>(pmf_to_cdf_kernel), dp, &max_dyn);  // once per device
+  if (rc != CAI_OK) return rc;
+  CAI_CHECK_ARG(smem <= static_cast<size_t>(max_dyn), "cai_pmf_to_quantized_cdf: row length %d needs too much shared memory", Lp);
   pmf_to_cdf_kernel<<<K, kPmfThreads, smem, static_cast<cudaStream_t>(stream_)>>>(pmf, pmf_len, tail, Lp, precision,
                                                                                   P, cdf, status);
   CAI_LAUNCH_CHECK();

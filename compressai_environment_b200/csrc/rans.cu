@@ -605,7 +605,9 @@ static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
   // SMs -- each CTA pins a copy of the table in shared memory -- and leave the rest of the chip to the
   // transform kernels running concurrently on other streams.
   int w = (B + dp.sm_count / 4 - 1) / (dp.sm_count / 4 > 0 ? dp.sm_count / 4 : 1);
-  if (const char *ov = getenv("CAI_CODER_WARPS")) { const int v = atoi(ov); if (v >= 1 && v <= kMaxWarpsPerCta) w = w > v ? w : v; } else if (w < 8) w = 8;
+  const int kw = knobs().coder_warps;
+  if (kw >= 1 && kw <= kMaxWarpsPerCta) w = w > kw ? w : kw;
+  else if (w < 8) w = 8;
   if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
   if (w > B) w = B < 1 ? 1 : B;
   int g = (B + w - 1) / w;
@@ -638,8 +640,10 @@ int cai_rans_encode_batch(cai_table_t t, const int32_t *symbols, const int32_t *
   plan_grid(dp, B, &warps, &grid);
   if (t->enc_in_smem) {
     const size_t smem = ((t->enc_bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kEncWarpBytes;
-    CAI_CUDA(cudaFuncSetAttribute(rans_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    int max_dyn = 0;
+    rc = optin_max_smem(reinterpret_cast<const void *>(rans_encode_kernel<true>), dp, &max_dyn);  // once per device
+    if (rc != CAI_OK) return rc;
+    CAI_CHECK_ARG(smem <= static_cast<size_t>(max_dyn), "cai_rans_encode_batch: table does not fit shared memory");
     rans_encode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, t->enc_bytes, symbols, indexes,
                                                                  str_begin, n_per_string, B, slots,
                                                                  slot_words, n_words, status);
@@ -694,8 +698,10 @@ int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *w
   const uint32_t bytes = static_cast<uint32_t>(t->blob_bytes);
   if (t->in_smem) {
     const size_t smem = ((bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kDecWarpBytes;
-    CAI_CUDA(cudaFuncSetAttribute(rans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    int max_dyn = 0;
+    rc = optin_max_smem(reinterpret_cast<const void *>(rans_decode_kernel<true>), dp, &max_dyn);  // once per device
+    if (rc != CAI_OK) return rc;
+    CAI_CHECK_ARG(smem <= static_cast<size_t>(max_dyn), "cai_rans_decode_batch: table does not fit shared memory");
     rans_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(t->blob, bytes, words, word_begin, word_count, indexes,
                                                                  str_begin, n_per_string, B, out, state,
                                                                  resume, status);

@@ -15,6 +15,8 @@
 //   inside symbol s0 (decode needs no search), freq == 0 means "search forward from s0".
 #include <cstdlib>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -46,6 +48,52 @@ int get_device_props(DeviceProps *out) {
   }
   *out = p;
   return CAI_OK;
+}
+
+int optin_max_smem(const void *kernel, const DeviceProps &dp, int *max_dynamic, int carveout) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void *>> done;
+  static std::set<std::pair<int, const void *>> carved;
+  std::lock_guard<std::mutex> lk(mu);
+  cudaFuncAttributes fa;
+  const std::pair<int, const void *> key(dp.device, kernel);
+  if (!done.count(key) || max_dynamic) {
+    CAI_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    const int lim = dp.max_smem_optin - static_cast<int>(fa.sharedSizeBytes);
+    if (!done.count(key)) {
+      CAI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      done.insert(key);
+    }
+    if (max_dynamic) *max_dynamic = lim;
+  }
+  if (carveout >= 0 && !carved.count(key)) {
+    CAI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    carved.insert(key);
+  }
+  return CAI_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+const Knobs &knobs() {
+  static const Knobs k = [] {
+    Knobs r;
+    r.conv_stages = env_int("CAI_CONV_STAGES", 0);
+    r.conv_generic = getenv("CAI_CONV_GENERIC") ? 1 : 0;
+    r.conv_carveout = env_int("CAI_CONV_CARVEOUT", -1);
+    r.conv_debug = env_int("CAI_CONV_DEBUG", 0);
+    r.patch_generic = getenv("CAI_PATCH_GENERIC") ? 1 : 0;
+    r.coder_warps = env_int("CAI_CODER_WARPS", 0);
+    r.lut_buckets = env_int("CAI_LUT_BUCKETS", 0);
+    r.table_smem_kb = env_int("CAI_TABLE_SMEM_KB", -1);
+    r.conv_persist = env_int("CAI_CONV_PERSIST", -1);
+    r.coder_lut_adapt = env_int("CAI_LUT_ADAPT", -1);
+    return r;
+  }();
+  return k;
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------
@@ -203,10 +251,11 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
   }
   h.off_lut = static_cast<uint32_t>(base);
   h.enc_bytes = h.off_lut;
-  // Shared memory budget: leave 40 KB for per-warp staging buffers (32 warps) and static smem.
-  const int64_t budget = static_cast<int64_t>(dp.max_smem_optin) - 40 * 1024;
+  // Shared memory budget: the coder kernels add 32 warps x 1280 B of staging, round the blob up to 128 B and own a
+  // few bytes of static shared memory (mbarrier); 1 KB covers the latter two.
+  const int64_t budget = static_cast<int64_t>(dp.max_smem_optin) - 32 * 1280 - 1024;
   int nb = 256;
-  if (const char *ov = getenv("CAI_LUT_BUCKETS")) { const int v = atoi(ov); if (v >= 1 && v <= 256 && (v & (v - 1)) == 0) nb = v; }
+  { const int v = knobs().lut_buckets; if (v >= 1 && v <= 256 && (v & (v - 1)) == 0) nb = v; }
   while (nb > 1 && static_cast<int64_t>(base) + static_cast<int64_t>(K) * nb * 8 > budget) nb >>= 1;
   const int in_smem = static_cast<int64_t>(base) + static_cast<int64_t>(K) * nb * 8 <= budget;
   if (!in_smem) nb = 256;  // tables live in L2; keep the LUT fine
@@ -214,7 +263,8 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
   int sh = 16;
   for (int t = nb; t > 1; t >>= 1) --sh;
   h.lut_shift = sh;
-  h.total_bytes = h.off_lut + static_cast<uint32_t>(K) * static_cast<uint32_t>(nb) * 8u;
+  // padded to 16 bytes: the blob is staged with cp.async.bulk, whose size must be a multiple of 16
+  h.total_bytes = (h.off_lut + static_cast<uint32_t>(K) * static_cast<uint32_t>(nb) * 8u + 15u) & ~15u;
 
   cai_table *t = new cai_table();
   e = cudaMalloc(&t->blob, h.total_bytes);
@@ -244,7 +294,7 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
   // CAI_TABLE_SMEM_KB: tables larger than this stay in global memory (L1 / L2) even if they would fit the CTA's
   // shared memory -- a coder CTA that stages a big table keeps the transform kernels' CTAs off its SM.
   int64_t cap = budget;
-  if (const char *ov = getenv("CAI_TABLE_SMEM_KB")) cap = static_cast<int64_t>(atoi(ov)) * 1024;
+  if (knobs().table_smem_kb >= 0) cap = static_cast<int64_t>(knobs().table_smem_kb) * 1024;
   t->in_smem = in_smem && static_cast<int64_t>(h.total_bytes) <= cap;
   t->enc_in_smem = static_cast<int64_t>(h.enc_bytes) <= budget && static_cast<int64_t>(h.enc_bytes) <= cap;
   t->device = dp.device;
