@@ -1,17 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the codec hot path (BASELINE.json: compress+decompress MP/s).
+"""bench.py -- headline benchmark of the codec hot path (BASELINE.json: compress+decompress MP/s and rANS Msym/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
 
 Workload (BASELINE.json configs[1], "C2"): bmshj2018-hyperprior q4 (N=128, M=192), `--batch` (default 256)
-synthetic 768x512 RGB images per GPU, random-init weights (seed 0) with the deterministic latent / scale
-amplification of SURVEY.md 8(d)(ii) so that the Gaussian-conditional coder sees non-degenerate symbols.
+synthetic 768x512 RGB images per GPU (seed = rank), random-init weights (seed 0) with the deterministic latent /
+scale amplification of SURVEY.md 8(d)(ii) so that the Gaussian-conditional coder sees non-degenerate symbols.
 One step = compress + decompress of the whole batch.  Prints ONE JSON line on rank 0.
 
+  parity   : gate run BEFORE any timing: the CPU oracle encodes sampled images' y / z symbols and
+             the bytes must equal ours; every string of the batch is decoded and the symbols must equal the
+             encoder's; device-path statuses are read; the public-API (host) path must reproduce the device path's
+             strings and reconstruction; the reconstruction is compared with a plain torch fp32 synthesis.
+             A failing gate exits non-zero and no value is printed.
   value    : device-resident pipeline (inputs in HBM, strings stay in HBM), CUDA-event timed, max over ranks
-  e2e      : the public API with HOST buffers: pinned images -> model.compress() -> bytes on the host ->
+  e2e      : the public API with HOST buffers: pinned images -> model.compress() -> strings on the host ->
              model.decompress() -> reconstruction on the host (H2D / D2H inside the timed region)
-  roofline : the rANS decode kernel (dominant kernel written in this repo), algorithmic bytes / CUDA-event time
+  roofline : conv_gemm_kernel, the tcgen05 implicit-GEMM transform kernel (dominant kernel by SM time): algorithmic
+             FLOPs / CUDA-event time; roofline_coder / roofline_index: the rANS decode and the fused index kernel
+  rans_c3  : the raw coder on BASELINE configs[2] (2^28 symbols per GPU, 4096 strings), every rank, beside the
+             reference's C++ coder timed on the box's host cores (1 core, and all cores through a process pool)
+  configs  : C1 (factorized q1, one image) and C4 (mbt2018-mean q8, one 3840x2176 frame) through the public API
   cpu_baseline : the UNMODIFIED reference (oracle/_ref) on the host cores, bounded sample of the same workload
 
 --impl reference times the reference's own CPU implementation (model.compress/decompress, torch CPU +
@@ -24,6 +33,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -40,23 +50,27 @@ GAIN_Y, GAIN_S = 64.0, 256.0
 VARIANTS = (("as_is", 1.0, 1.0), ("trained_rate_0.5bpp", 4.0, 32.0))
 METRIC = "compress+decompress throughput, bmshj2018-hyperprior q4, 768x512 images"
 UNIT = "MP/s"
+DTYPE = "bf16x3 (fp32 operands split into bf16 hi+lo, three tcgen05 MMAs per product, fp32 accumulate)"
+XHAT_TOL = 1e-3  # north_star: reconstructions within max-abs 1e-3 of an fp32 implementation
 
 
-def amplify(net):
+def amplify(net, gy=None, gs=None):
     import torch
 
+    gy = GAIN_Y if gy is None else gy
+    gs = GAIN_S if gs is None else gs
     with torch.no_grad():
-        net.g_a[6].weight.mul_(GAIN_Y)
-        net.g_a[6].bias.mul_(GAIN_Y)
-        net.h_s[4].weight.mul_(GAIN_S)
-        net.h_s[4].bias.mul_(GAIN_S)
+        net.g_a[6].weight.mul_(gy)
+        net.g_a[6].bias.mul_(gy)
+        net.h_s[4].weight.mul_(gs)
+        net.h_s[4].bias.mul_(gs)
 
 
-def make_images(batch, seed=0):
+def make_images(batch, seed=0, h=H, w=W):
     import torch
 
     g = torch.Generator().manual_seed(seed)
-    return torch.rand(batch, 3, H, W, generator=g)
+    return torch.rand(batch, 3, h, w, generator=g)
 
 
 class ClockSampler:
@@ -98,17 +112,80 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------------------
-def reference_arm(args, rank):
-    """The UNMODIFIED reference on the host cores (oracle/_ref), same model state, bounded sample per step."""
+# ---- host placement -------------------------------------------------------------------------------------------
+def _parse_cpulist(text):
+    out = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.update(range(int(a), int(b or a) + 1))
+    return out
+
+
+def gpu_local_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when that cannot be determined."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return None
+        dom, rest = out.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        with open(path) as f:
+            cpus = _parse_cpulist(f.read())
+        return cpus or None
+    except Exception:
+        return None
+
+
+def plan_rank_cpus(allowed, local_sets, rank):
+    """Disjoint CPU sets for the ranks of one box.  ``allowed``: CPUs this job may use; ``local_sets[r]``: CPUs local
+    to rank r's GPU (or None).  Ranks whose GPUs share a NUMA node split that node's allowed CPUs evenly (in rank
+    order); without topology information the allowed CPUs are split evenly across all ranks.  Returns rank's set."""
+    allowed = sorted(allowed)
+    world = len(local_sets)
+    if world <= 1 or len(allowed) < world:
+        return set(allowed)
+    usable = [sorted(set(s) & set(allowed)) if s else None for s in local_sets]
+    if any(u is None or len(u) == 0 for u in usable):
+        usable = [allowed] * world
+    mine = usable[rank]
+    peers = [r for r in range(world) if usable[r] == mine]
+    if len(mine) < len(peers):
+        return set(mine)
+    k = peers.index(rank)
+    per = len(mine) // len(peers)
+    return set(mine[k * per:(k + 1) * per])
+
+
+def pin_rank(rank, world, local, mode):
+    """Bind this rank (and the pinned memory it allocates afterwards: first touch) to CPUs next to its GPU."""
+    info = {"mode": mode, "cpus": None, "numa_aware": False}
+    if mode == "off" or (mode == "auto" and world == 1) or not hasattr(os, "sched_setaffinity"):
+        info["cpus"] = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        return info
+    allowed = os.sched_getaffinity(0)
+    local_sets = [gpu_local_cpus(i) for i in range(world)]
+    info["numa_aware"] = all(s for s in local_sets)
+    mine = plan_rank_cpus(allowed, local_sets, rank)
+    if mine:
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            mine = allowed
+    info["cpus"] = len(mine)
+    return info
+
+
+# ---- reference arms (CPU) -------------------------------------------------------------------------------------
+def _ref_model():
     import torch
 
     from oracle import oracle as orc
 
     if not orc.have_ref():
         orc.build_ref()
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     orc.import_ref()
     from compressai.zoo import bmshj2018_hyperprior as ref_hyperprior
 
@@ -116,6 +193,16 @@ def reference_arm(args, rank):
     net = ref_hyperprior(quality=4, pretrained=False).eval()
     amplify(net)
     net.update(force=True)
+    return net
+
+
+def reference_arm(args, rank):
+    """The UNMODIFIED reference on the host cores (oracle/_ref), same model state, bounded sample per step."""
+    import torch
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    net = _ref_model()
     sample = max(1, args.ref_sample)
     x = make_images(sample)
     times = []
@@ -151,18 +238,12 @@ def cpu_baseline_sample(n_images):
 
     from oracle import oracle as orc
 
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if not orc.have_ref() and not orc.build_ref():
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "oracle/_ref missing"}
     prev = torch.get_num_threads()
     torch.set_num_threads(cores)
-    orc.import_ref()
-    from compressai.zoo import bmshj2018_hyperprior as ref_hyperprior
-
-    torch.manual_seed(0)
-    net = ref_hyperprior(quality=4, pretrained=False).eval()
-    amplify(net)
-    net.update(force=True)
+    net = _ref_model()
     x = make_images(n_images)
     with torch.no_grad():
         net.compress(x[:1])  # warm-up
@@ -173,7 +254,94 @@ def cpu_baseline_sample(n_images):
         dt = time.perf_counter() - t0
     torch.set_num_threads(prev)
     return {"value": n_images * H * W / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"{n_images} images in batches of 8, compress+decompress ({dt:.1f} s), all host threads"}, enc
+            "sample": f"{n_images} images in batches of 8, compress+decompress ({dt:.1f} s), all host threads"}
+
+
+# C3 on the host: the reference's C++ coder through its own Python binding (lists in, bytes out), as
+# EntropyModel.compress / decompress drive it (compressai/entropy_models/entropy_models.py:259-267, :313-323).
+_C3_N = 65536
+_cpu_tabs = None
+
+
+def _cpu_c3_string(seed):
+    """(symbols, indexes) of one C3 string: uniform table rows, symbols ~ round(N(0,1) * scale_table[row])."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 64, _C3_N).astype(np.int32)
+    sym = np.rint(rng.standard_normal(_C3_N) * _cpu_tabs["scale"][idx]).astype(np.int32)
+    return sym.tolist(), idx.tolist()
+
+
+def _cpu_c3_init(tabs):
+    global _cpu_tabs
+    _cpu_tabs = tabs
+    from oracle import oracle as orc
+
+    orc.import_ref()
+
+
+def _cpu_c3_work(seeds):
+    """Encode then decode the strings of `seeds`; returns (encode seconds, decode seconds, n strings)."""
+    from compressai import ans
+
+    t = _cpu_tabs
+    enc, dec = ans.RansEncoder(), ans.RansDecoder()
+    te = td = 0.0
+    for s in seeds:
+        sym, idx = _cpu_c3_string(s)
+        t0 = time.perf_counter()
+        data = enc.encode_with_indexes(sym, idx, t["cdf"], t["len"], t["off"])
+        t1 = time.perf_counter()
+        out = dec.decode_with_indexes(data, idx, t["cdf"], t["len"], t["off"])
+        t2 = time.perf_counter()
+        assert out == sym
+        te += t1 - t0
+        td += t2 - t1
+    return te, td, len(seeds)
+
+
+def cpu_coder_leg(per_worker=12):
+    """Reference rANS coder on C3-shaped strings: 1 core, then all cores through multiprocessing.Pool
+    (BASELINE.md 3.3).  Runs in a process that never touches CUDA (bench.py --cpu-coder-leg)."""
+    import multiprocessing as mp
+
+    import torch
+
+    from oracle import oracle as orc
+
+    if not orc.have_ref() and not orc.build_ref():
+        return {"error": "oracle/_ref missing"}
+    orc.import_ref()
+    from compressai.entropy_models import GaussianConditional
+    from compressai.models.google import get_scale_table
+
+    torch.set_num_threads(1)
+    gc = GaussianConditional(None)
+    gc.update_scale_table(get_scale_table())
+    tabs = {"cdf": gc._quantized_cdf.tolist(), "len": gc._cdf_length.reshape(-1).int().tolist(),
+            "off": gc._offset.reshape(-1).int().tolist(), "scale": gc.scale_table.numpy().astype("float64")}
+    _cpu_c3_init(tabs)
+    _cpu_c3_work([0])  # warm-up
+    te, td, n = _cpu_c3_work([1, 2, 3])
+    one = {"encode_msym_s": n * _C3_N / te / 1e6, "decode_msym_s": n * _C3_N / td / 1e6}
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with mp.get_context("fork").Pool(cores, initializer=_cpu_c3_init, initargs=(tabs,)) as pool:
+        pool.map(_cpu_c3_work, [[100 + w] for w in range(cores)])  # start every worker, warm
+        jobs = [[1000 + w * per_worker + j for j in range(per_worker)] for w in range(cores)]
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_c3_work, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    n_all = sum(r[2] for r in res)
+    fe = sum(r[0] for r in res) / max(1e-9, sum(r[0] + r[1] for r in res))  # share of the wall spent encoding
+    return {"workload": f"C3-shaped strings of {_C3_N} symbols, 64-row Gaussian table, reference compressai.ans "
+                        "through its list API (pybind conversions included, as the reference calls it)",
+            "cores": cores, "one_core": one,
+            "all_cores": {"encode_msym_s": n_all * _C3_N / (wall * fe) / 1e6,
+                          "decode_msym_s": n_all * _C3_N / (wall * (1 - fe)) / 1e6,
+                          "encode_plus_decode_msym_s": n_all * _C3_N / wall / 1e6, "strings": n_all,
+                          "wall_s": wall, "how": "multiprocessing.Pool(cores), each worker encodes then decodes "
+                                                 f"{per_worker} strings; encode / decode split by summed worker time"}}
 
 
 def interval_union(intervals):
@@ -207,15 +375,131 @@ def shard_throughput(units_per_rank, ms, world):
     return world * units_per_rank / (ms * 1e-3)
 
 
+# ---- parity gate ----------------------------------------------------------------------------------------------
+def torch_synthesis(net, y_hat, dtype):
+    """Plain torch restatement of g_s (conv_transpose2d + IGDN by its definition, layers/gdn.py:77-92 of the
+    reference) in ``dtype``: float64 is the ground truth of the gate, float32 (TF32 off) the yardstick that shows
+    how far an ordinary fp32 implementation lands from it on the same inputs."""
+    import torch
+    import torch.nn.functional as F
+
+    from compressai_environment_b200.layers import GDN
+    from compressai_environment_b200.transforms import ConvTranspose2d
+
+    x = y_hat.contiguous().to(dtype)
+    for m in net.g_s:
+        if isinstance(m, ConvTranspose2d):
+            x = F.conv_transpose2d(x, m.weight.to(dtype), m.bias.to(dtype), stride=m.stride, padding=m.padding,
+                                   output_padding=m.output_padding)
+        elif isinstance(m, GDN):
+            beta, gamma = (t.to(dtype) for t in m.effective_params())
+            C = beta.numel()
+            norm = F.conv2d(x * x, gamma.reshape(C, C, 1, 1), beta)
+            x = x * (torch.sqrt(norm) if m.inverse else torch.rsqrt(norm))
+        else:
+            raise RuntimeError(type(m).__name__)
+    return x.clamp(0, 1)
+
+
+def parity_gate(net, x_dev, x_host, mb, n_oracle=4):
+    """Checks run before any timing; returns the report dict, ``report["ok"]`` False on any failure.
+    The oracle (oracle/, test infrastructure) is used here as the CHECKER only."""
+    import numpy as np
+    import torch
+
+    from compressai_environment_b200 import coder, kernels
+    from oracle import oracle as orc
+
+    rep = {"ok": False}
+    gc, eb = net.gaussian_conditional, net.entropy_bottleneck
+    gc_t, eb_t = gc._table(), eb._table()
+    B = x_dev.size(0)
+    with torch.no_grad():
+        # device-resident path, exactly what the timed loop runs
+        enc = net.compress_to_device(x_dev)
+        dec = net.decompress_from_device(enc["strings"], enc["shape"])
+        torch.cuda.synchronize()
+        st = torch.cat([s.reshape(-1) for s in dec["status"]]).cpu()
+        rep["device_path_statuses_nonzero"] = int((st != 0).sum())
+        x_hat_dev = dec["x_hat"]
+        # every string decoded, symbols compared with the encoder's; oracle on the first images
+        n_sym_bad = 0
+        n_strings = 0
+        first = None
+        for k, i in enumerate(range(0, B, mb)):
+            y_sym, y_idx, z_sym, z_idx, _ = net._analysis_chunk(x_dev[i:i + mb])
+            ye, ze = enc["strings"][0][k], enc["strings"][1][k]
+            y_dec = coder.decode(gc_t, None, y_idx, device_words=ye.device_words())
+            z_dec = coder.decode(eb_t, None, z_idx, device_words=ze.device_words())
+            n_sym_bad += int((y_dec != y_sym).sum()) + int((z_dec != z_sym).sum())
+            n_strings += 2 * y_sym.size(0)
+            if first is None:
+                first = [t[:n_oracle].cpu().numpy() for t in (y_sym, y_idx, z_sym, z_idx)] + [ye.to_bytes(), ze.to_bytes()]
+        rep["strings_decoded"] = n_strings
+        rep["decoded_symbols_differing"] = n_sym_bad
+        ysym, yidx, zsym, zidx, ybytes, zbytes = first
+        ytabs = [t.cpu().numpy() for t in (gc._quantized_cdf, gc._cdf_length, gc._offset)]
+        ztabs = [t.cpu().numpy() for t in (eb._quantized_cdf, eb._cdf_length, eb._offset)]
+        bad_bytes = 0
+        for b in range(min(n_oracle, ysym.shape[0])):
+            ry = orc.rans_encode(ysym[b], yidx[b], *ytabs)
+            rz = orc.rans_encode(zsym[b], zidx[b], *ztabs)
+            bad_bytes += int(ry != ybytes[b]) + int(rz != zbytes[b])
+            bad_bytes += int(not np.array_equal(orc.rans_decode(ybytes[b], yidx[b], *ytabs), ysym[b].ravel()))
+        rep["oracle_images"] = min(n_oracle, ysym.shape[0])
+        rep["oracle_strings_differing"] = bad_bytes
+        rep["oracle_y_bytes"] = [len(s) for s in ybytes[:n_oracle]]
+        # public API with host tensors: same strings, same reconstruction
+        out_host = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+        enc_h = net.compress(x_host)
+        dec_h = net.decompress(enc_h["strings"], enc_h["shape"], out=out_host)
+        torch.cuda.synchronize()
+        dev_y = [s for e in enc["strings"][0] for s in e.to_bytes()]
+        dev_z = [s for e in enc["strings"][1] for s in e.to_bytes()]
+        rep["host_vs_device_strings_differing"] = (sum(int(a != b) for a, b in zip(enc_h["strings"][0], dev_y))
+                                                   + sum(int(a != b) for a, b in zip(enc_h["strings"][1], dev_z))
+                                                   + abs(len(dev_y) - len(enc_h["strings"][0])))
+        rep["host_vs_device_x_hat_max_abs"] = float((dec_h["x_hat"].to(x_hat_dev.device) - x_hat_dev).abs().max())
+        # floating point yardstick: torch fp32 synthesis of the first images' decoded latents
+        nb = min(2, B)
+        y_sym0 = net._analysis_chunk(x_dev[:mb])[0][:nb].contiguous()
+        y_hat = kernels.dequantize(y_sym0, None, None, (nb, M_CH, H // 16, W // 16), torch.contiguous_format)
+        ref64 = torch_synthesis(net, y_hat, torch.float64)
+        ref32 = torch_synthesis(net, y_hat, torch.float32)
+        rep["x_hat_vs_fp64_max_abs"] = float((ref64 - x_hat_dev[:nb].double()).abs().max())
+        rep["torch_fp32_vs_fp64_max_abs"] = float((ref64 - ref32.double()).abs().max())
+        # bar: within north_star's 1e-3 of the exact result, or -- where fp32 itself cannot hold 1e-3 on these
+        # amplified random-init activations -- no further from it than 4x a plain cuDNN fp32 synthesis is
+        rep["x_hat_tolerance"] = max(XHAT_TOL, 4.0 * rep["torch_fp32_vs_fp64_max_abs"])
+        rep["x_hat_finite_in_range"] = bool(torch.isfinite(x_hat_dev).all() and float(x_hat_dev.min()) >= 0.0
+                                            and float(x_hat_dev.max()) <= 1.0)
+    rep["ok"] = (rep["device_path_statuses_nonzero"] == 0 and n_sym_bad == 0 and bad_bytes == 0
+                 and rep["host_vs_device_strings_differing"] == 0 and rep["host_vs_device_x_hat_max_abs"] == 0.0
+                 and rep["x_hat_vs_fp64_max_abs"] <= rep["x_hat_tolerance"] and rep["x_hat_finite_in_range"])
+    return rep
+
+
+# ---- the GPU arm ----------------------------------------------------------------------------------------------
 def ours(args, rank, world):
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cpu_coder = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # reference coder on the host cores, in a CUDA-free child process, before this process creates its context
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-coder-leg"], capture_output=True,
+                               text=True, timeout=300, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+            cpu_coder = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            cpu_coder = {"error": f"{type(e).__name__}: {e}"}
+    placement = pin_rank(rank, world, local, args.pin_cores)  # after the CPU leg: that one uses every core
+
     import torch
     import torch.distributed as dist
 
-    import compressai_environment_b200 as cai
     from compressai_environment_b200 import _lib, coder, transforms
     from compressai_environment_b200.zoo import bmshj2018_hyperprior
 
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.set_num_threads(1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -230,36 +514,43 @@ def ours(args, rank, world):
     net.update(force=True)
 
     B, mb = args.batch, min(args.micro_batch, args.batch)
-    x_host = make_images(B).pin_memory()
+    x_host = make_images(B, seed=rank).pin_memory()  # every rank codes its own images
     x_dev = x_host.to(dev)
     mp_step = B * H * W / 1e6
-
     net.micro_batch = mb
+
+    # ---- parity gate (before any timing); every rank checks its own shard
+    parity = parity_gate(net, x_dev, x_host, mb)
+    fails = max_over_ranks([0.0 if parity["ok"] else 1.0], dev, world)[0]
+    if fails:
+        if not parity["ok"]:
+            print(f"[bench rank {rank}] PARITY GATE FAILED: {json.dumps(parity)}", file=sys.stderr, flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        raise SystemExit(3)
 
     def step_device():
         enc = net.compress_to_device(x_dev)
         dec = net.decompress_from_device(enc["strings"], enc["shape"])
-        return [(enc, dec)]
+        return enc, dec
 
     def variant_value(gy, gs, steps=6):
         """Device-resident MP/s of the same step for another stream rate (same loop as the headline number)."""
         torch.manual_seed(0)
         vnet = bmshj2018_hyperprior(quality=4)
-        with torch.no_grad():
-            vnet.g_a[6].weight.mul_(gy); vnet.g_a[6].bias.mul_(gy)
-            vnet.h_s[4].weight.mul_(gs); vnet.h_s[4].bias.mul_(gs)
+        amplify(vnet, gy, gs)
         vnet = vnet.to(dev).eval()
         vnet.update(force=True)
         vnet.micro_batch = mb
 
         def one():
             enc = vnet.compress_to_device(x_dev)
-            vnet.decompress_from_device(enc["strings"], enc["shape"])
-            return enc
+            dec = vnet.decompress_from_device(enc["strings"], enc["shape"])
+            return enc, dec
 
         with torch.no_grad():
             for _ in range(3):
-                enc = one()
+                enc, dec = one()
             torch.cuda.synchronize()
             users = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.inflight))]
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -268,15 +559,16 @@ def ours(args, rank, world):
                 u.wait_event(a)
             for i in range(steps):
                 with torch.cuda.stream(users[i % len(users)]):
-                    enc = one()
+                    enc, dec = one()
             for u in users:
                 torch.cuda.current_stream().wait_event(u.record_event())
             b.record()
             torch.cuda.synchronize()
+            coder.check_status(dec["status"])
             y_bits = float(sum(int(e.n_words.sum().item()) for e in enc["strings"][0])) * 32 / (B * M_CH * (H // 16) * (W // 16))
         return a.elapsed_time(b) / steps, y_bits
 
-    n_e2e_workers = max(1, args.e2e_inflight)
+    n_e2e_workers = max(1, min(args.e2e_inflight, (placement["cpus"] or 1) + 1))
     out_hosts = [torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory() for _ in range(n_e2e_workers)]
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(n_e2e_workers)]
 
@@ -284,10 +576,11 @@ def ours(args, rank, world):
     free_slots = queue.SimpleQueue()
     for i in range(n_e2e_workers):
         free_slots.put(i)
+    host_cpu_s = []
 
     def step_e2e(_=0):
-        """One request through the PUBLIC API with host buffers: pinned images -> H2D -> model.compress() (bytes on
-        the host) -> model.decompress(bytes) -> reconstruction copied to a caller-provided pinned buffer."""
+        """One request through the PUBLIC API with host buffers: pinned images -> H2D -> model.compress() (strings on
+        the host) -> model.decompress(strings) -> reconstruction copied to a caller-provided pinned buffer."""
         slot = free_slots.get()   # one stream + one pinned output buffer per request in flight
         try:
             return _step_e2e(slot)
@@ -296,6 +589,7 @@ def ours(args, rank, world):
 
     def _step_e2e(slot):
         torch.cuda.set_device(local)
+        c0 = time.thread_time()
         with torch.cuda.stream(e2e_streams[slot]), torch.no_grad():
             if args.e2e_device_io:   # caller moves the whole batch itself: x.to(device) / x_hat.cpu()
                 xb = x_host.to(dev, non_blocking=True)
@@ -309,10 +603,11 @@ def ours(args, rank, world):
             nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
             h2d = x_host.numel() * 4 + nbytes
             d2h = nbytes + out_hosts[slot].numel() * 4
+        host_cpu_s.append(time.thread_time() - c0)
         return h2d, d2h, nbytes
 
     def run_e2e(n_steps):
-        """n_steps requests, up to two in flight (two host threads, one CUDA stream each), like a serving loop."""
+        """n_steps requests, `n_e2e_workers` in flight (host threads, one CUDA stream each), like a serving loop."""
         if n_e2e_workers == 1:
             for _ in range(n_steps):
                 r = step_e2e(0)
@@ -347,12 +642,14 @@ def ours(args, rank, world):
         e0.record()
         for u in users:
             u.wait_event(e0)
+        timed_status = []
         for i in range(args.steps):
             if users:
                 with torch.cuda.stream(users[i % len(users)]):
-                    outs = step_device()
+                    enc, dec = step_device()
             else:
-                outs = step_device()
+                enc, dec = step_device()
+            timed_status += dec["status"]
         for u in users:
             torch.cuda.current_stream().wait_event(u.record_event())
         e1.record()
@@ -362,30 +659,30 @@ def ours(args, rank, world):
         conv_timing, transforms.TIMING = transforms.TIMING, None
         ms = e0.elapsed_time(e1) / args.steps
         clocks = sampler.stop() if rank == 0 else None
+        coder.check_status(timed_status, "timed loop")  # every string of every timed step coded cleanly
 
-        # roofline of the dominant kernel written here: rANS decode of the y strings
+        # coder launches of the timed region: rANS decode / encode of the y strings of one micro-batch
         dec_ms = sorted(a.elapsed_time(b) for a, b in timing.get("rans_decode_kernel", []))
         enc_ms = sorted(a.elapsed_time(b) for a, b in timing.get("rans_encode_kernel", []))
-        y_encs = outs[-1][0]["strings"][0]
+        y_encs = enc["strings"][0]
         n_sym_y = mb * M_CH * (H // 16) * (W // 16)       # symbols per coder launch (one micro-batch)
         payload = int(y_encs[-1].n_words.sum().item()) * 4
         # decode: 4 B/sym index read + payload read + 4 B/sym symbol write
         alg_bytes = 8 * n_sym_y + payload
         big = [t for t in dec_ms if t >= 0.5 * dec_ms[-1]] if dec_ms else []
         dec_avg = sum(big) / len(big) if big else None
+        big_e = [t for t in enc_ms if t >= 0.5 * enc_ms[-1]] if enc_ms else []
+        enc_avg = sum(big_e) / len(big_e) if big_e else None
 
-        # dominant kernel by time: the tcgen05 implicit-GEMM transform kernel.  Sum of its launch durations per step
-        # (CUDA events on the launching streams; launches on the analysis and synthesis streams may overlap, which
-        # only makes the summed time -- and the reported rate -- pessimistic).
+        # dominant kernel by time: the tcgen05 implicit-GEMM transform kernel.  Launches of different requests overlap
+        # (analysis of step i+1 runs beside the synthesis of step i and share the SMs), which inflates every
+        # individual duration; the time during which AT LEAST ONE conv_gemm launch is executing (union of the event
+        # intervals) is the kernel's real occupancy of the timed region.
         conv_iv = sorted((e0.elapsed_time(a), e0.elapsed_time(b)) for a, b in conv_timing.get("conv_gemm_kernel", []))
         conv_ms = [b - a for a, b in conv_iv]
         conv_ms_step = sum(conv_ms) / args.steps if conv_ms else None
         conv_launches_step = len(conv_ms) / args.steps if conv_ms else 0
-        # launches of different requests overlap (analysis of step i+1 runs beside the synthesis of step i and share
-        # the SMs), which inflates every individual duration; the time during which AT LEAST ONE conv_gemm launch is
-        # executing (union of the event intervals) is the kernel's real occupancy of the timed region
-        conv_union = interval_union(conv_iv)
-        conv_union_step = conv_union / args.steps if conv_ms else None
+        conv_union_step = interval_union(conv_iv) / args.steps if conv_ms else None
         # algorithmic FLOPs (2 * MAC): compress g_a + h_a + h_s = 35.31 GFLOP,
         # decompress h_s + g_s = 34.24 GFLOP per 768x512 image
         conv_flops_step = B * (35.31e9 + 34.24e9)
@@ -393,10 +690,18 @@ def ours(args, rank, world):
         # e2e through the public API with host buffers
         run_e2e(n_e2e_workers)  # warm-up (allocator pools of the worker streams, pinned staging buffers)
         barrier()
+        host_cpu_s.clear()
         t0 = time.perf_counter()
         h2d, d2h, _ = run_e2e(args.e2e_steps)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        e2e_host_cpu = sum(host_cpu_s) / max(1, len(host_cpu_s))
+        barrier()
+
+        # C3 raw coder on EVERY rank (each codes its own 2^28 symbols), max over ranks
+        c3 = c3_raw_coder(net, dev, seed=1234 + rank)
+        c3_enc_ms, c3_dec_ms = max_over_ranks([c3["encode_ms"], c3["decode_ms"]], dev, world)
+        c3_ok = max_over_ranks([0.0 if c3["round_trip_exact"] else 1.0], dev, world)[0] == 0.0
 
         iso = isolated_kernels(net, mb, B, dev) if rank == 0 else None
         variants = {}
@@ -406,8 +711,10 @@ def ours(args, rank, world):
                 v_ms = max_over_ranks([v_ms], dev, world)[0]
                 variants[name] = {"value": shard_throughput(mp_step, v_ms, world), "unit": UNIT, "ms_per_step": v_ms,
                                   "gain_y": gy, "gain_s": gs, "y_bits_per_symbol": v_bits, "steps": 6}
+        extra = other_configs(dev) if (rank == 0 and not args.no_variants) else None
+        barrier()
 
-    ms, e2e_ms = max_over_ranks([ms, e2e_s * 1e3], dev, world)
+    ms, e2e_ms, e2e_host_cpu = max_over_ranks([ms, e2e_s * 1e3, e2e_host_cpu], dev, world)
 
     if rank != 0:
         if world > 1:
@@ -422,35 +729,40 @@ def ours(args, rank, world):
     hbm = peaks.get("hbm_gbs", 6650.0)
     tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
     conv_tf = conv_flops_step / (conv_union_step * 1e-3) / 1e12 if conv_union_step else None
-    traffic = None
-    try:  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/README.md)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        try:  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/README.md)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"]
+            traffic_src = name
+            break
+        except Exception:
+            pass
     achieved = alg_bytes / (dec_avg * 1e-3) / 1e9 if dec_avg else None
     cpu = {"value": None}
     if not args.no_cpu_baseline:
         try:
-            cpu, _ = cpu_baseline_sample(args.cpu_sample)
+            cpu = cpu_baseline_sample(args.cpu_sample)
         except Exception as e:  # the baseline must never take the GPU line down
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    n_c3 = 4096 * 65536
     line = {
         "metric": METRIC, "value": shard_throughput(mp_step, ms, world), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": "C2 bmshj2018-hyperprior q4 (N=128,M=192) 768x512, random-init seed 0, amplified",
-                   "batch_per_gpu": B, "micro_batch": mb, "gain_y": GAIN_Y, "gain_s": GAIN_S,
+                   "batch_per_gpu": B, "micro_batch": mb, "gain_y": GAIN_Y, "gain_s": GAIN_S, "image_seed": "rank",
                    "l2": "inputs_larger_than_L2 (302 MB images, >1 GB activations per micro-batch)",
                    "y_bits_per_symbol": payload * 8 / n_sym_y, "parallelism": f"batch-sharded x{world}, no collective",
-                   "steps_in_flight": max(1, args.inflight)},
+                   "steps_in_flight": max(1, args.inflight), "host_placement": placement},
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": shard_throughput(mp_step, e2e_ms, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
-                "requests_in_flight": n_e2e_workers},
+                "requests_in_flight": n_e2e_workers, "host_cpu_ms_per_request": e2e_host_cpu * 1e3},
         "gpu_launches": launches,
         "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv / deconv / fused GDN)", "bound": "tensor",
                      "achieved": conv_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (conv_tf / tpeak) if conv_tf else None,
-                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_conv_traffic.json)",
+                     "traffic": traffic, "traffic_unit": f"DRAM bytes per launch (ncu, profiles/{traffic_src})",
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else
                                                       "fallback 1.4 PFLOP/s sustained"),
                      "alg_flops_per_launch": conv_flops_step / conv_launches_step if conv_launches_step else None,
@@ -465,24 +777,133 @@ def ours(args, rank, world):
                                   "how": "same kernel timed alone, L2 flushed, median of 5"} if iso else None,
                      "note": "algorithmic fp32-equivalent FLOPs; the kernel issues 3 bf16 MMAs per product "
                              "(split hi/lo operands), so tensor-pipe work is 3x the algorithmic figure"},
-        "roofline_coder": {"kernel": "rans_decode_kernel (y strings)", "bound": "hbm", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": (achieved / hbm) if achieved else None, "traffic": None,
-                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                     "avg_launch_ms": dec_avg, "alg_bytes_per_launch": alg_bytes,
-                     "encode_avg_launch_ms": (sum(enc_ms[len(enc_ms) // 2:]) / max(1, len(enc_ms) - len(enc_ms) // 2))
-                     if enc_ms else None},
+        "roofline_coder": {"kernel": "rans_decode_kernel (y strings of one micro-batch)", "bound": "hbm",
+                           "achieved": achieved, "peak": hbm,
+                           "unit": "GB/s", "frac": (achieved / hbm) if achieved else None, "traffic": None,
+                           "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                           "avg_launch_ms": dec_avg, "alg_bytes_per_launch": alg_bytes,
+                           "encode_avg_launch_ms": enc_avg,
+                           "symbols_per_string": n_sym_y // mb,
+                           "decode_ns_per_symbol": dec_avg * 1e6 / (n_sym_y // mb) if dec_avg else None,
+                           "encode_ns_per_symbol": enc_avg * 1e6 / (n_sym_y // mb) if enc_avg else None},
         "roofline_index": {"kernel": "gc_qi_nhwc_kernel (fused quantize + build_indexes, one step's y/scales)",
                            "bound": "hbm", "achieved": iso["index"]["gbs"], "peak": hbm, "unit": "GB/s",
                            "frac": iso["index"]["gbs"] / hbm, "traffic": None, "avg_launch_ms": iso["index"]["ms"],
                            "alg_bytes_per_launch": iso["index"]["alg_bytes"],
                            "how": "timed alone, L2 flushed, median of 5"} if iso else None,
-        "rans_c3": iso["c3"] if iso else None,
+        "rans_c3": {"workload": "C3 raw coder: 4096 strings x 65,536 symbols per GPU, 64-row Gaussian table",
+                    "unit": "Msym/s", "n_gpus": world,
+                    "encode_msym_s": world * n_c3 / c3_enc_ms / 1e3, "decode_msym_s": world * n_c3 / c3_dec_ms / 1e3,
+                    "encode_ms": c3_enc_ms, "decode_ms": c3_dec_ms, "bits_per_symbol": c3["bits_per_symbol"],
+                    "encode_alg_gbs_per_gpu": c3["alg_bytes"] / c3_enc_ms / 1e6,
+                    "decode_alg_gbs_per_gpu": c3["alg_bytes"] / c3_dec_ms / 1e6,
+                    "encode_hbm_frac": c3["alg_bytes"] / c3_enc_ms / 1e6 / hbm,
+                    "decode_hbm_frac": c3["alg_bytes"] / c3_dec_ms / 1e6 / hbm,
+                    "round_trip_exact": c3_ok, "reference_cpu": cpu_coder},
         "variants": variants,
+        "configs": extra,
         "cpu_baseline": cpu,
     }
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+def c3_raw_coder(model, dev, seed):
+    """C3 (BASELINE.json configs[2]): raw coder, 2^28 symbols = 4096 strings x 65,536, the model's 64-row Gaussian
+    table, symbols ~ round(N(0, 1) * scale_table[idx]) (4.6 bit/symbol, no escapes); decoded symbols checked."""
+    import torch
+
+    from compressai_environment_b200 import coder
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, n=3):
+        fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    gc = model.gaussian_conditional
+    tab = gc.scale_table.to(dev).float().contiguous()
+    Bs, ns = 4096, 65536
+    cidx = torch.randint(0, int(tab.numel()), (Bs, ns), generator=gen, device=dev, dtype=torch.int32)
+    csym = torch.round(torch.randn((Bs, ns), generator=gen, device=dev) * tab[cidx.long()]).to(torch.int32)
+    table = gc._table()
+    enc = coder.encode(table, csym, cidx)
+    words = enc.device_words()
+    dec = coder.decode(table, None, cidx, device_words=words)
+    ok = bool(torch.equal(dec, csym)) and int(enc.status.abs().max()) == 0
+    del dec
+    e_ms = timed(lambda: coder.encode(table, csym, cidx))
+    d_ms = timed(lambda: coder.decode(table, None, cidx, device_words=words, status_out=[]))
+    payload = int(enc.n_words.sum().item()) * 4
+    return {"encode_ms": e_ms, "decode_ms": d_ms, "bits_per_symbol": payload * 8 / (Bs * ns),
+            "alg_bytes": 8 * Bs * ns + payload, "round_trip_exact": ok}
+
+
+def other_configs(dev):
+    """C1 and C4 of BASELINE.json through the public API (device tensors in, strings on the host, device tensor out),
+    one request at a time: MP/s = image pixels / (compress + decompress wall time), as eval_model times it."""
+    import torch
+
+    from compressai_environment_b200.zoo import bmshj2018_factorized, mbt2018_mean
+
+    out = {}
+
+    def run(net, x, reps):
+        with torch.no_grad():
+            for _ in range(2):
+                enc = net.compress(x)
+                dec = net.decompress(enc["strings"], enc["shape"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                enc = net.compress(x)
+                dec = net.decompress(enc["strings"], enc["shape"])
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+        assert dec["x_hat"].shape == x.shape
+        nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
+        return dt, nbytes
+
+    try:
+        torch.manual_seed(0)
+        net = bmshj2018_factorized(1)
+        with torch.no_grad():
+            net.g_a[6].weight.mul_(64.0)
+            net.g_a[6].bias.mul_(64.0)
+        net = net.to(dev).eval()
+        net.update(force=True)
+        x = make_images(1).to(dev)
+        dt, nb = run(net, x, 10)
+        out["C1_factorized_q1_1x768x512"] = {"value": H * W / 1e6 / dt, "unit": UNIT, "ms_per_image": dt * 1e3,
+                                             "bpp": nb * 8 / (H * W), "gain_y": 64.0, "requests_in_flight": 1}
+        del net, x
+        torch.manual_seed(0)
+        net = mbt2018_mean(8)
+        with torch.no_grad():
+            for m in (net.g_a[6], net.h_s[4]):
+                m.weight.mul_(64.0)
+                m.bias.mul_(64.0)
+        net = net.to(dev).eval()
+        net.update(force=True)
+        x = make_images(1, h=2176, w=3840).to(dev)
+        dt, nb = run(net, x, 3)
+        out["C4_mbt2018_mean_q8_1x3840x2176"] = {"value": 2176 * 3840 / 1e6 / dt, "unit": UNIT, "ms_per_frame": dt * 1e3,
+                                                 "bpp": nb * 8 / (2176 * 3840), "gain_y": 64.0, "gain_s": 64.0,
+                                                 "requests_in_flight": 1,
+                                                 "note": "one 10.4 M-symbol y string: a single serial rANS chain"}
+        del net, x
+        torch.cuda.empty_cache()
+    except Exception as e:  # secondary figures never take the headline down
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 def isolated_kernels(model, mb, B, dev):
@@ -491,7 +912,9 @@ def isolated_kernels(model, mb, B, dev):
     micro-batch) and the fused quantize+index kernel on one step's y / scales (channels-last, as the transforms
     produce them)."""
     import torch
-    from compressai_environment_b200 import transforms as T, _lib
+
+    from compressai_environment_b200 import _lib
+    from compressai_environment_b200 import transforms as T
     from compressai_environment_b200.kernels import CAI_LAYOUT_NHWC
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -526,28 +949,6 @@ def isolated_kernels(model, mb, B, dev):
             (H // 16) * (W // 16), _lib.ptr(sym), _lib.ptr(idx), _lib.current_stream()), "cai_gc_quantize_index"))
         out["index"] = {"ms": ms, "gbs": 16 * n / ms / 1e6, "alg_bytes": 16 * n}
         del y, sc, sym, idx
-        # C3 (BASELINE.json configs[2]): raw coder, 2^28 symbols = 4096 strings x 65,536, the model's 64-row Gaussian
-        # table, symbols ~ round(N(0, 1) * scale_table[idx]) (4.6 bit/symbol, no escapes); decoded symbols checked
-        from compressai_environment_b200 import coder
-        gen = torch.Generator(device=dev).manual_seed(1234)
-        gc = model.gaussian_conditional
-        Bs, ns = 4096, 65536
-        cidx = torch.randint(0, int(tab.numel()), (Bs, ns), generator=gen, device=dev, dtype=torch.int32)
-        csym = torch.round(torch.randn((Bs, ns), generator=gen, device=dev) * tab[cidx.long()]).to(torch.int32)
-        table = gc._table()
-        enc = coder.encode(table, csym, cidx)
-        words = enc.device_words()
-        dec = coder.decode(table, None, cidx, device_words=words)
-        ok = bool(torch.equal(dec, csym))
-        del dec
-        e_ms = timed(lambda: coder.encode(table, csym, cidx), 3)
-        d_ms = timed(lambda: coder.decode(table, None, cidx, device_words=words), 3)
-        payload = int(enc.n_words.sum().item()) * 4
-        out["c3"] = {"workload": "C3 raw coder: 4096 strings x 65,536 symbols, 64-row Gaussian table",
-                     "encode_msym_s": Bs * ns / e_ms / 1e3, "decode_msym_s": Bs * ns / d_ms / 1e3,
-                     "encode_ms": e_ms, "decode_ms": d_ms, "bits_per_symbol": payload * 8 / (Bs * ns),
-                     "encode_alg_gbs": (8 * Bs * ns + payload) / e_ms / 1e6,
-                     "decode_alg_gbs": (8 * Bs * ns + payload) / d_ms / 1e6, "round_trip_exact": ok}
     return out
 
 
@@ -565,13 +966,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-device-io", action="store_true",
                     help="e2e: copy the whole batch to the device / back around the API calls instead of passing host tensors")
-    ap.add_argument("--no-variants", action="store_true", help="skip the as-is / trained-rate variants of the workload")
+    ap.add_argument("--no-variants", action="store_true", help="skip the as-is / trained-rate / C1 / C4 variants")
     ap.add_argument("--gain-y", type=float, default=GAIN_Y, help="scale of the last g_a layer (stream rate, see GAIN_Y)")
     ap.add_argument("--gain-s", type=float, default=GAIN_S, help="scale of the last h_s layer")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (user streams) in the device-timed loop")
     ap.add_argument("--e2e-inflight", type=int, default=5, help="requests in flight (host threads) in the e2e loop")
+    ap.add_argument("--pin-cores", default="auto", choices=["auto", "on", "off"],
+                    help="bind each rank to its own CPUs next to its GPU (auto: only when there are several ranks)")
+    ap.add_argument("--cpu-coder-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     globals().update(GAIN_Y=args.gain_y, GAIN_S=args.gain_s)
+    if args.cpu_coder_leg:
+        print(json.dumps(cpu_coder_leg()), flush=True)
+        return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
@@ -583,5 +990,27 @@ def main():
         print(json.dumps(line), flush=True)
 
 
+def _entry():
+    """Failures must be legible under torchrun: print the rank and the traceback before the elastic agent tears the
+    other ranks down, and let torch's @record write the error file it reports."""
+    try:
+        from torch.distributed.elastic.multiprocessing.errors import record
+    except Exception:
+        record = lambda f: f  # noqa: E731
+
+    @record
+    def run():
+        try:
+            main()
+        except SystemExit:
+            raise
+        except BaseException:
+            print(f"[bench rank {os.environ.get('RANK', 0)} pid {os.getpid()}] FAILED:\n{traceback.format_exc()}",
+                  file=sys.stderr, flush=True)
+            raise
+
+    run()
+
+
 if __name__ == "__main__":
-    main()
+    _entry()

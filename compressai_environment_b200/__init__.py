@@ -29,3 +29,11 @@ def get_entropy_coder():
 def available_entropy_coders():
     """Return the list of available entropy coders."""
     return _available_entropy_coders
+
+
+def invalidate_caches(module):
+    """Drop the packed weights / tables cached below ``module`` (needed only after editing parameters through
+    ``tensor.data``, which bypasses the version counters the caches are keyed on)."""
+    from ._cache import invalidate_caches as _inv
+
+    _inv(module)

@@ -95,12 +95,56 @@ def to_host(t: torch.Tensor) -> torch.Tensor:
     return host
 
 
+class PackedStrings(list):
+    """The byte strings of a batch as zero-copy views of ONE pinned host buffer.
+
+    A ``list`` whose items are read-only ``memoryview`` slices (``len()``, ``==`` against ``bytes``, ``file.write``,
+    ``b"".join`` and ``bytes(s)`` all work as with the ``bytes`` objects the reference returns); the strings sit
+    back to back, word aligned, in ``host`` (int32, pinned) at word offsets ``begin[i] .. begin[i+1]``.  Building it
+    costs no per-string copy, and ``decode`` uploads an intact ``PackedStrings`` (or a slice of one) with a single
+    asynchronous copy straight from the pinned buffer -- no repacking on the host."""
+
+    def __init__(self, host: torch.Tensor, begin: np.ndarray):
+        self.host, self.begin = host, np.asarray(begin, dtype=np.int64)
+        raw = memoryview(host.numpy().view(np.uint8)).toreadonly()
+        super().__init__(raw[int(a) * 4:int(e) * 4] for a, e in zip(self.begin[:-1], self.begin[1:]))
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            a, e, step = key.indices(len(self))
+            if step == 1 and self.intact():
+                e = max(a, e)
+                return PackedStrings(self.host, self.begin[a:e + 1])
+            return list(self)[key]
+        return super().__getitem__(key)
+
+    def intact(self) -> bool:
+        """False once the list was edited so that it no longer mirrors ``host`` / ``begin``."""
+        n = len(self)
+        if n != len(self.begin) - 1:
+            return False
+        for i in ((0, n - 1) if n else ()):
+            v = super().__getitem__(i)
+            if not isinstance(v, memoryview) or v.nbytes != int(self.begin[i + 1] - self.begin[i]) * 4:
+                return False
+        return True
+
+    def to_bytes(self) -> List[bytes]:
+        return [bytes(v) for v in self]
+
+
+def as_strings(strings):
+    """A sequence of byte strings as something ``decode`` indexes cheaply (PackedStrings kept as they are)."""
+    return strings if isinstance(strings, PackedStrings) else list(strings)
+
+
 def _raise_status(status: torch.Tensor, what: str):
+    """Every non-zero per-string status is an error -- including 6 (the decoder consumed more words than the string
+    holds): a valid stream is consumed exactly, so running past the end means truncation or corruption."""
     st = to_host(status)
     bad = torch.nonzero(st != 0).reshape(-1)
-    hard = [int(i) for i in bad if int(st[i]) != 6]
-    if hard:
-        i = hard[0]
+    if bad.numel():
+        i = int(bad[0])
         raise ValueError(f"{what}: string {i}: {_lib.STATUS_TEXT.get(int(st[i]), int(st[i]))}")
 
 
@@ -143,14 +187,15 @@ class EncodedBatch:
         return out
 
 
-def batches_to_bytes(batches: Sequence[EncodedBatch]) -> List[List[bytes]]:
-    """``to_bytes()`` for several EncodedBatches with TWO host synchronisations in total instead of two per batch:
-    all sizes come back in one copy, every batch is compacted into its own range of one packed buffer, and one
-    device->host copy brings all strings back.  Batches may live on different streams (``batch.stream``)."""
+def batches_to_host(batches: Sequence[EncodedBatch]):
+    """Bring the strings of several EncodedBatches to the host with TWO host synchronisations in total: all sizes
+    come back in one copy, every batch is compacted into its own range of one packed device buffer, and one
+    device->host copy lands all strings in one pinned buffer.  Batches may live on different streams
+    (``batch.stream``).  Returns ``(host int32 pinned tensor, [word-offset array (n_b + 1) per batch])``."""
     batches = list(batches)
     live = [b for b in batches if b.n_words.numel()]
     if not live:
-        return [[] for _ in batches]
+        return torch.empty(0, dtype=torch.int32), [np.zeros(1, np.int64) for _ in batches]
     dev = live[0].slots.device
     cur = torch.cuda.current_stream(dev)
     for b in live:
@@ -183,22 +228,23 @@ def batches_to_bytes(batches: Sequence[EncodedBatch]) -> List[List[bytes]]:
     host = torch.empty(max(grand, 1), dtype=torch.int32, pin_memory=True)
     host.copy_(packed, non_blocking=True)
     cur.synchronize()                                                                                      # sync 2
-    raw = host.numpy().view(np.uint8)
-    ends = np.cumsum(nw_all) * 4
-    flat, a = [], 0
-    for e in ends.tolist():
-        flat.append(raw[a:e].tobytes())
-        a = e
-    out, a = [], 0
+    ends = np.concatenate([[0], np.cumsum(nw_all)])
+    begins, a = [], 0
     it = iter(counts)
     for b in batches:
         if b.n_words.numel():
             c = next(it)
-            out.append(flat[a:a + c])
+            begins.append(ends[a:a + c + 1].copy())
             a += c
         else:
-            out.append([])
-    return out
+            begins.append(ends[a:a + 1].copy())
+    return host, begins
+
+
+def batches_to_bytes(batches: Sequence[EncodedBatch]) -> List[List[bytes]]:
+    """``to_bytes()`` for several EncodedBatches (see :func:`batches_to_host`), as real ``bytes`` objects."""
+    host, begins = batches_to_host(batches)
+    return [PackedStrings(host, bg).to_bytes() for bg in begins]
 
 
 def encode(table: CdfTable, symbols: torch.Tensor, indexes: torch.Tensor) -> EncodedBatch:
@@ -221,7 +267,14 @@ def encode(table: CdfTable, symbols: torch.Tensor, indexes: torch.Tensor) -> Enc
 
 
 def strings_to_device(strings: Sequence[bytes], device) -> tuple:
-    """Concatenate byte strings (zero padded to whole words) -> (uint32-as-int32 words, int64 begins)."""
+    """Concatenate byte strings (zero padded to whole words) -> (uint32-as-int32 words, int64 begins).
+    An intact :class:`PackedStrings` is uploaded as it is: one asynchronous copy from its pinned buffer."""
+    if isinstance(strings, PackedStrings) and strings.intact() and len(strings):
+        lo, hi = int(strings.begin[0]), int(strings.begin[-1])
+        words = strings.host[lo:max(hi, lo + 1)].to(device, non_blocking=True)
+        wb_host = torch.empty(len(strings.begin), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        wb_host.numpy()[:] = strings.begin - lo
+        return words, wb_host.to(device, non_blocking=True), (strings.host, wb_host)
     lens = np.array([(len(s) + 3) // 4 for s in strings], dtype=np.int64)
     begin = np.zeros(len(strings) + 1, dtype=np.int64)
     np.cumsum(lens, out=begin[1:])
@@ -236,8 +289,9 @@ def strings_to_device(strings: Sequence[bytes], device) -> tuple:
     if total == 0:
         hv[:] = 0
     words = host.view(torch.int32).to(device, non_blocking=True)
-    wb = torch.from_numpy(begin).to(device, non_blocking=True)
-    return words, wb, host
+    wb_host = torch.empty(len(begin), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+    wb_host.numpy()[:] = begin
+    return words, wb_host.to(device, non_blocking=True), (host, wb_host)
 
 
 def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, state: Optional[torch.Tensor] = None,
@@ -269,8 +323,7 @@ def decode(table: CdfTable, strings: Sequence[bytes], indexes: torch.Tensor, sta
               "cai_rans_decode_batch")
     if status_out is not None:
         status_out.append(status)
-    elif keep is not None:
-        torch.cuda.current_stream(dev).synchronize()
+    else:  # no deferred check requested: surface decoder errors here (host strings and device words alike)
         _raise_status(status, "rANS decode")
     return out
 

@@ -27,7 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
-from .. import _CXX, coder, kernels
+from .. import _CXX, _cache, coder, kernels
 from .._lib import (CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, CaiError, check, current_stream, lib, ptr, require_cuda)
 from ..ops import LowerBound
 
@@ -81,7 +81,7 @@ def _common_layout(ref: Tensor, *others: Optional[Tensor]):
     return layout, outs
 
 
-class EntropyModel(nn.Module):
+class EntropyModel(_cache.CacheOwner, nn.Module):
     r"""Entropy model base class (reference :99-325).
 
     Args:
@@ -106,13 +106,11 @@ class EntropyModel(nn.Module):
         self.register_buffer("_offset", torch.IntTensor())
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
-        self._table_cache = None
 
     def __getstate__(self):
         attributes = self.__dict__.copy()
         attributes["entropy_coder"] = self.entropy_coder.name
-        attributes["_table_cache"] = None
-        attributes.pop("_scalar_cache", None)
+        attributes.pop("_cai_cache", None)  # packed tables / host scalars are rebuilt on demand
         return attributes
 
     def __setstate__(self, state):
@@ -137,13 +135,8 @@ class EntropyModel(nn.Module):
     def _cached_scalar(owner, buf):
         """Host copy of a 1-element buffer, refreshed only when the buffer changes (avoids a device->host sync
         per call: the codec path must stay asynchronous so that chunks can overlap)."""
-        key = (buf.data_ptr(), buf._version)
-        cache = owner.__dict__.setdefault("_scalar_cache", {})
-        hit = cache.get(id(buf))
-        if hit is None or hit[0] != key:
-            hit = (key, float(buf.item()))
-            cache[id(buf)] = hit
-        return hit[1]
+        return _cache.cached(owner, f"scalar{id(buf)}", _cache.tensor_key(buf), lambda: float(buf.item()),
+                             synchronous=True)
 
     def _lik_bound(self) -> float:
         if not self.use_likelihood_bound:
@@ -218,11 +211,9 @@ class EntropyModel(nn.Module):
     def _table(self) -> coder.CdfTable:
         """Packed table for the current buffers; rebuilt when update() / load_state_dict changed them."""
         q, l, o = self._quantized_cdf, self._cdf_length, self._offset
-        key = (q.data_ptr(), q._version, tuple(q.shape), l.data_ptr(), l._version, o.data_ptr(), o._version,
-               str(q.device))
-        if self._table_cache is None or self._table_cache[0] != key:
-            self._table_cache = (key, coder.CdfTable(q, l, o))
-        return self._table_cache[1]
+        # cai_table_create synchronises its stream: the blob is visible to every stream when it returns
+        return _cache.cached(self, "table", _cache.tensor_key(q, l, o), lambda: coder.CdfTable(q, l, o),
+                             synchronous=True)
 
     # ---- coding -----------------------------------------------------------------------------------------
     def _validate_compress(self, inputs, indexes):
@@ -272,7 +263,7 @@ class EntropyModel(nn.Module):
         require_cuda(indexes, "indexes")
         N = indexes.size(0)
         idx = indexes.to(torch.int32).contiguous().reshape(N, -1)
-        sym = coder.decode(self._table(), list(strings), idx)
+        sym = coder.decode(self._table(), coder.as_strings(strings), idx)
         shape = tuple(indexes.shape) if indexes.dim() > 2 else (N, indexes.size(1), 1)
         m = means
         if m is not None:
@@ -454,7 +445,16 @@ class EntropyBottleneck(EntropyModel):
     def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
         """inputs (C, 1, L) -> logits (C, 1, L) (reference :436-455) with one kernel."""
         require_cuda(inputs, "inputs")
-        return _BottleneckLogits.apply(inputs, self._tparams(True), self.filters)
+        if stop_gradient or not torch.is_grad_enabled():
+            return _BottleneckLogits.apply(inputs, self._tparams(True), self.filters)
+        # Gradient w.r.t. the density parameters requested (no caller on the codec / training path does: forward()
+        # and _likelihood() go through cai_eb_forward / cai_eb_backward): parameter-sized torch ops, same recurrence.
+        logits = inputs
+        for i in range(len(self.filters) + 1):
+            logits = torch.matmul(F.softplus(getattr(self, f"_matrix{i:d}")), logits) + getattr(self, f"_bias{i:d}")
+            if i < len(self.filters):
+                logits = logits + torch.tanh(getattr(self, f"_factor{i:d}")) * torch.tanh(logits)
+        return logits
 
     def update(self, force: bool = False) -> bool:
         # reference :389-429
@@ -552,7 +552,7 @@ class EntropyBottleneck(EntropyModel):
         N, C = output_size[0], output_size[1]
         HW = int(np.prod(output_size[2:])) if len(output_size) > 2 else 1
         idx = kernels.channel_indexes(N, C, HW, dev)
-        sym = coder.decode(self._table(), None if device_words is not None else list(strings), idx,
+        sym = coder.decode(self._table(), None if device_words is not None else coder.as_strings(strings), idx,
                            device_words=device_words)
         shape = output_size if len(output_size) > 2 else (N, C, 1)
         out = kernels.dequantize(sym, None, self._get_medians(), shape, memory_format)
@@ -670,6 +670,6 @@ class GaussianConditional(EntropyModel):
         self._check_cdf_length()
         self._check_offsets_size()
         _, idx = kernels.gc_quantize_index(None, scales, None, self.scale_table, self._bound_scale())
-        sym = coder.decode(self._table(), None if device_words is not None else list(strings), idx,
+        sym = coder.decode(self._table(), None if device_words is not None else coder.as_strings(strings), idx,
                            device_words=device_words)
         return kernels.dequantize(sym, means, None, tuple(scales.shape), memory_format)

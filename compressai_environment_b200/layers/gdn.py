@@ -9,12 +9,13 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from .._cache import CacheOwner
 from ..ops.parametrizers import NonNegativeParametrizer
 
 __all__ = ["GDN"]
 
 
-class GDN(nn.Module):
+class GDN(CacheOwner, nn.Module):
     def __init__(self, in_channels: int, inverse: bool = False, beta_min: float = 1e-6, gamma_init: float = 0.1):
         super().__init__()
         beta_min = float(beta_min)
@@ -28,7 +29,6 @@ class GDN(nn.Module):
         self.gamma_reparam = NonNegativeParametrizer()
         gamma = gamma_init * torch.eye(in_channels)
         self.gamma = nn.Parameter(self.gamma_reparam.init(gamma))
-        self._packed = None
 
     def effective_params(self):
         """(beta [C], gamma [C, C]) after the non-negative reparametrisation (tiny tensors)."""
@@ -37,7 +37,7 @@ class GDN(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         from .. import transforms
 
-        if torch.is_grad_enabled() and (x.requires_grad or self.beta.requires_grad):
+        if torch.is_grad_enabled() and (x.requires_grad or self.beta.requires_grad or self.gamma.requires_grad):
             beta, gamma = self.effective_params()
             return transforms.gdn(x, beta, gamma, self.inverse)
         return transforms.run_stack([self], x)

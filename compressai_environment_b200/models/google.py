@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
-from .. import _lib, coder, kernels
+from .. import _cache, _lib, coder, kernels
 from ..entropy_models import EntropyBottleneck, GaussianConditional
 from ..layers import GDN
 from ..transforms import TransformStack
@@ -66,12 +66,16 @@ class CompressionModel(nn.Module):
                 continue
             rv = m.update(force=force)
             updated |= rv
+        # update() is the point after which the coder must see the current parameters: drop every derived cache
+        # (packed weights, packed tables, host scalars), including ones that `.data` edits could not invalidate
+        _cache.invalidate_caches(self)
         return updated
 
     def load_state_dict(self, state_dict):
         update_registered_buffers(self.entropy_bottleneck, "entropy_bottleneck",
                                   ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
         super().load_state_dict(state_dict)
+        _cache.invalidate_caches(self)
 
 
 class FactorizedPrior(CompressionModel):
@@ -294,18 +298,28 @@ class ScaleHyperprior(CompressionModel):
         return {"strings": [y_encs, z_encs], "shape": shape}
 
     def compress(self, x):
+        """Reference interface (models/google.py:302-312): ``{"strings": [y_strings, z_strings], "shape": ...}``.
+        The two string lists are ``coder.PackedStrings``: lists of read-only zero-copy views of one pinned host
+        buffer (use ``bytes(s)`` for an owning copy); ``decompress`` uploads them without repacking."""
         out = self.compress_to_device(x)
         y_encs, z_encs = out["strings"]
-        lists = coder.batches_to_bytes(list(y_encs) + list(z_encs))  # two host syncs for the whole request
-        ys = [s for lst in lists[:len(y_encs)] for s in lst]
-        zs = [s for lst in lists[len(y_encs):] for s in lst]
-        return {"strings": [ys, zs], "shape": out["shape"]}
+        host, begins = coder.batches_to_host(list(y_encs) + list(z_encs))  # two host syncs for the whole request
+        ny = len(y_encs)
+
+        def joined(bgs):  # consecutive batches occupy consecutive ranges of the packed buffer
+            if not bgs:
+                return coder.PackedStrings(host, [0])
+            return coder.PackedStrings(host, [int(bgs[0][0])] + [int(v) for bg in bgs for v in bg[1:]])
+
+        return {"strings": [joined(begins[:ny]), joined(begins[ny:])], "shape": out["shape"]}
 
     @torch.no_grad()
     def _decompress_chunks(self, chunks, shape, device, statuses=None, out=None):
         """chunks: list of (coder_stream, y_words, z_words, n) with *_words = (strings | None, device_words | None)."""
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         eb_t, gc_t = eb._table(), gc._table()
+        if statuses is None:
+            statuses = []  # never check inside the pipeline: that would synchronise the host per chunk
         S = self._streams(device, 1)
         syn, hyp = S["syn"], S["hyp"]
         main = torch.cuda.current_stream(device)
@@ -337,16 +351,27 @@ class ScaleHyperprior(CompressionModel):
                 done = ck.record_event()  # "syn" must NOT wait here: that would serialise the chunks' decodes
                 y_sym.record_stream(syn)
             pending.append((y_sym, means_hat, tuple(scales_hat.shape), done))
-        outs = []
+        x_hat = None
         with torch.cuda.stream(syn):
             syn.wait_event(hyp.record_event())  # means_hat / shapes produced on "hyp"
             row = 0
+            if out is None and len(pending) > 1:
+                # device result: every micro-batch's last layer writes straight into its rows of ONE batch tensor
+                # (a torch.cat of the per-chunk outputs re-copied 2.4 GB per 256-image step)
+                total = sum(p[2][0] for p in pending)
+                hy, wy = pending[0][2][2], pending[0][2][3]  # g_s upsamples the latent grid by 16
+                x_hat = torch.empty((total, 3, 16 * hy, 16 * wy), dtype=torch.float32, device=device)
             for y_sym, means_hat, shp, done in pending:
                 syn.wait_event(done)
                 y_hat = kernels.dequantize(y_sym, means_hat, None, shp, _CL)
-                xc = self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True)
+                dst = x_hat[row:row + shp[0]] if x_hat is not None else None
+                xc = self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True, out=dst)
+                if dst is not None and xc.data_ptr() != dst.data_ptr():
+                    dst.copy_(xc)  # last layer without the direct-destination path (more than 4 output channels)
                 if out is None:
-                    outs.append(xc)
+                    if x_hat is None:
+                        x_hat = xc
+                    row += shp[0]
                 else:
                     # host output buffer (serving path): this micro-batch goes home while the next one is synthesised
                     d2h = S["d2h"]
@@ -357,12 +382,10 @@ class ScaleHyperprior(CompressionModel):
                     row += xc.size(0)
         if out is not None:
             main.wait_event(S["d2h"].record_event())
-            return {"x_hat": out}
-        with torch.cuda.stream(syn):
-            x_hat = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+            return {"x_hat": out, "status": statuses}
         main.wait_event(syn.record_event())
         x_hat.record_stream(main)
-        return {"x_hat": x_hat}
+        return {"x_hat": x_hat, "status": statuses}
 
     @torch.no_grad()
     def decompress(self, strings, shape, out=None):
@@ -380,7 +403,8 @@ class ScaleHyperprior(CompressionModel):
         coder_streams = self._take_coder_streams(S, len(starts))
         chunks = []
         for k, i in enumerate(starts):
-            ys, zs = list(strings[0][i:i + self.micro_batch]), list(strings[1][i:i + self.micro_batch])
+            ys, zs = strings[0][i:i + self.micro_batch], strings[1][i:i + self.micro_batch]
+            ys, zs = (v if isinstance(v, coder.PackedStrings) else list(v) for v in (ys, zs))
             chunks.append((coder_streams[k], (ys, None), (zs, None), len(ys)))
         statuses = []
         if out is not None and (out.is_cuda or out.dim() != 4 or out.size(0) != n or out.dtype != torch.float32):
@@ -388,17 +412,22 @@ class ScaleHyperprior(CompressionModel):
         res = self._decompress_chunks(chunks, shape, dev, statuses, out)
         torch.cuda.current_stream(dev).synchronize()  # one sync per call: surface decoder errors like the reference would
         coder.check_status(statuses)
-        return res
+        return {"x_hat": res["x_hat"]}
 
     @torch.no_grad()
     def decompress_from_device(self, enc, shape):
+        """decompress() of strings still in HBM (``compress_to_device``).  Fully asynchronous; the per-string decoder
+        statuses come back under ``"status"`` (device tensors) for ``coder.check_status`` once the caller has
+        synchronised -- nothing is checked here."""
         y_encs, z_encs = enc
         dev = y_encs[0].slots.device
-        chunks = []
+        chunks, statuses = [], []
         for ye, ze in zip(y_encs, z_encs):
             with torch.cuda.stream(ye.stream):  # the word offsets are derived from n_words on the coder stream
                 chunks.append((ye.stream, (None, ye.device_words()), (None, ze.device_words()), int(ye.n_words.numel())))
-        return self._decompress_chunks(chunks, shape, dev, [])
+        for ye, ze in zip(y_encs, z_encs):  # encoder statuses (slot overflow, bad index) travel with the result too
+            statuses += [ye.status, ze.status]
+        return self._decompress_chunks(chunks, shape, dev, statuses)
 
 
 class MeanScaleHyperprior(ScaleHyperprior):

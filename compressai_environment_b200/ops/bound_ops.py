@@ -1,36 +1,45 @@
-"""``LowerBound``: ``max(x, bound)`` whose gradient passes when ``x >= bound`` or when the gradient pushes
-``x`` up (compressai/ops/bound_ops.py:36-80).  On the hot path the bound and its gate are folded into the
-fused likelihood / GDN kernels; this module form serves parameters (tiny tensors) and API parity."""
+"""``LowerBound`` -- a clamp-from-below whose gradient is gated instead of zeroed.
+
+Behaviour contract (what compressai/ops/bound_ops.py:36-80 of the reference defines and its checkpoints rely on):
+``y = max(x, bound)``; the incoming gradient reaches ``x`` wherever ``x`` already satisfies the bound OR the
+gradient would move ``x`` upwards (negative gradient); elsewhere it is dropped.  ``bound`` is a one-element buffer
+named ``bound`` so that reference ``state_dict`` keys (``...lower_bound.bound``) line up.
+
+On the hot path this gate is folded into the fused likelihood / GDN kernels (csrc/likelihood.cu, csrc/gdn.cu);
+the module form below only ever sees parameter-sized tensors (C or C x C) and scalars.
+"""
 import torch
 import torch.nn as nn
 from torch import Tensor
 
 
 class LowerBoundFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, bound):
-        ctx.save_for_backward(x, bound)
-        return torch.max(x, bound)
+    """Autograd node of :class:`LowerBound`: forward ``maximum``, backward the gated pass-through."""
 
     @staticmethod
-    def backward(ctx, grad_output):
+    def forward(ctx, x: Tensor, bound: Tensor) -> Tensor:
+        ctx.save_for_backward(x, bound)
+        return torch.maximum(x, bound)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
         x, bound = ctx.saved_tensors
-        keep = (x >= bound) | (grad_output < 0)
-        return keep * grad_output, None
+        inside = x.ge(bound)          # the clamp is inactive
+        pushes_up = g.lt(0)           # a descent step would raise x back towards the feasible side
+        return torch.where(inside.logical_or(pushes_up), g, torch.zeros_like(g)), None
 
 
 class LowerBound(nn.Module):
+    """``max(x, bound)`` with the gated gradient above.  ``bound`` is fixed at construction."""
+
     bound: Tensor
 
     def __init__(self, bound: float):
         super().__init__()
-        self.register_buffer("bound", torch.Tensor([float(bound)]))
+        self.register_buffer("bound", torch.tensor([float(bound)], dtype=torch.float32))
 
-    @torch.jit.unused
-    def lower_bound(self, x):
+    def forward(self, x: Tensor) -> Tensor:
         return LowerBoundFunction.apply(x, self.bound)
 
-    def forward(self, x):
-        if torch.jit.is_scripting():
-            return torch.max(x, self.bound)
-        return self.lower_bound(x)
+    def extra_repr(self) -> str:
+        return f"bound={float(self.bound):g}" if self.bound.numel() == 1 and not self.bound.is_meta else ""

@@ -28,7 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
-from . import _lib
+from . import _cache, _lib
 from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, ConvDesc, check, current_stream, lib, ptr, require_cuda
 
 _BK = 32
@@ -38,7 +38,7 @@ _BK = 32
 TIMING = None
 
 
-class Conv2d(nn.Module):
+class Conv2d(_cache.CacheOwner, nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=5, stride=2, padding=None):
         super().__init__()
         self.in_channels, self.out_channels = int(in_channels), int(out_channels)
@@ -47,7 +47,6 @@ class Conv2d(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels))
         self.reset_parameters()
-        self._packed = None
 
     def reset_parameters(self):  # same init as nn.Conv2d
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -64,7 +63,7 @@ class Conv2d(nn.Module):
         return f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}"
 
 
-class ConvTranspose2d(nn.Module):
+class ConvTranspose2d(_cache.CacheOwner, nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=5, stride=2, output_padding=1, padding=None):
         super().__init__()
         self.in_channels, self.out_channels = int(in_channels), int(out_channels)
@@ -74,7 +73,6 @@ class ConvTranspose2d(nn.Module):
         self.weight = nn.Parameter(torch.empty(in_channels, out_channels, kernel_size, kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels))
         self.reset_parameters()
-        self._packed = None
 
     def reset_parameters(self):  # same init as nn.ConvTranspose2d (fan_in computed on dim 1)
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -227,14 +225,12 @@ class _Layer:
         self.cin, self.cout, self.geom = cin, cout, geom
 
 
-def _param_key(*ps):
-    return tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
-
-
 def _prep_conv(m: "Conv2d") -> _Layer:
-    key = _param_key(m.weight, m.bias)
-    if m._packed is not None and m._packed[0] == key:
-        return m._packed[1]
+    """Packed layer of a conv module; cached per parameter version and published across streams (_cache.py)."""
+    return _cache.cached(m, "packed", _cache.tensor_key(m.weight, m.bias), lambda: _build_conv(m), m.weight.device)
+
+
+def _build_conv(m: "Conv2d") -> _Layer:
     k, s, p = m.kernel_size, m.stride, m.padding
     w = m.weight.detach().float()
     cout, cin = w.shape[0], w.shape[1]
@@ -255,14 +251,14 @@ def _prep_conv(m: "Conv2d") -> _Layer:
         bn = _choose_bn(cp)
         lay = _Layer("conv", pack_weights(_pad_taps(wt, cp, kp), bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
                      (k, s, p))
-    m._packed = (key, lay)
     return lay
 
 
 def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
-    key = _param_key(m.weight, m.bias)
-    if m._packed is not None and m._packed[0] == key:
-        return m._packed[1]
+    return _cache.cached(m, "packed", _cache.tensor_key(m.weight, m.bias), lambda: _build_deconv(m), m.weight.device)
+
+
+def _build_deconv(m: "ConvTranspose2d") -> _Layer:
     k, s, p, op = m.kernel_size, m.stride, m.padding, m.output_padding
     w = m.weight.detach().float()
     cin, cout = w.shape[0], w.shape[1]
@@ -292,15 +288,14 @@ def _prep_deconv(m: "ConvTranspose2d") -> _Layer:
                 phases.append(taps)
                 blobs.append(pack_weights(_pad_taps(torch.stack(ws, 0), cp, kp), bn, taps.glen) if ws else None)
         lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op))
-    m._packed = (key, lay)
     return lay
 
 
 def _prep_gdn(m) -> _Layer:
-    key = _param_key(m.beta, m.gamma)
-    cached = getattr(m, "_packed", None)
-    if cached is not None and cached[0] == key:
-        return cached[1]
+    return _cache.cached(m, "packed", _cache.tensor_key(m.beta, m.gamma), lambda: _build_gdn(m), m.beta.device)
+
+
+def _build_gdn(m) -> _Layer:
     with torch.no_grad():
         beta, gamma = m.effective_params()
     C = gamma.shape[0]
@@ -309,7 +304,6 @@ def _prep_gdn(m) -> _Layer:
     # padded channels: gamma = 0, beta = 1 -> out = 0 * rsqrt(1) = 0
     lay = _Layer("igdn" if m.inverse else "gdn", pack_weights(_pad_taps(gamma.detach().float().reshape(1, C, C), cp, cp), bn),
                  _pad_vec(beta, cp, 1.0), [[(0, 0)]], bn, cp, cp, None)
-    m._packed = (key, lay)
     return lay
 
 
@@ -395,7 +389,7 @@ def _run_conv(m, x, act, want, clamp=None, gdn=None):
     return o
 
 
-def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None):
+def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None, dst=None):
     lay = _prep_deconv(m)
     dev = m.weight.device
     if not isinstance(x, Planes):
@@ -407,7 +401,12 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None):
         _launch(x, lay.packed, None, [(0, 0)], lay.bn, npad, x.H, x.W, x.H, x.W, 1, 0, 0, 1, 0, None, cols, None, None,
                 None)
         if final_layout_nchw:
-            out = torch.empty((x.N, lay.cout, Ho, Wo), dtype=torch.float32, device=dev)
+            if dst is not None:  # caller-provided destination (a contiguous slice of a batch tensor)
+                if tuple(dst.shape) != (x.N, lay.cout, Ho, Wo) or not dst.is_contiguous() or dst.dtype != torch.float32:
+                    raise _lib.CaiError(f"out must be a contiguous float32 tensor of shape {(x.N, lay.cout, Ho, Wo)}")
+                out = dst
+            else:
+                out = torch.empty((x.N, lay.cout, Ho, Wo), dtype=torch.float32, device=dev)
             layout = CAI_LAYOUT_NCHW
         else:
             out = torch.empty((x.N, Ho, Wo, lay.cout), dtype=torch.float32, device=dev)
@@ -445,11 +444,12 @@ def _run_gdn(m, x: Planes, sq: Planes, want):
     return o
 
 
-def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw_out: bool = False):
+def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw_out: bool = False, out=None):
     """Run a conv / GDN / activation stack on the fused kernels (inference).  ``x`` is an fp32 tensor (logical
     NCHW, any memory format) or ``Planes``.  Returns the fp32 output as a logical-NCHW tensor stored channels-last
     (or true NCHW when the last layer is the 3-channel col2im with ``nchw_out``); with ``want_abs`` also returns
-    the split planes of |output| for the following hyper-analysis stack."""
+    the split planes of |output| for the following hyper-analysis stack.  ``out`` (only with ``nchw_out`` and a
+    3-channel last layer): preallocated contiguous NCHW destination the last layer writes into."""
     from .layers.gdn import GDN
 
     i, n = 0, len(mods)
@@ -498,7 +498,8 @@ def run_stack(mods: List[nn.Module], x, want_abs: bool = False, clamp=None, nchw
             if isinstance(m, Conv2d):
                 o = _run_conv(m, cur, act, want, clamp if last else None)
             else:
-                o = _run_deconv(m, cur, act, want, clamp if last else None, final_layout_nchw=nchw_out and last)
+                o = _run_deconv(m, cur, act, want, clamp if last else None, final_layout_nchw=nchw_out and last,
+                                dst=out if (nchw_out and last) else None)
                 is_nchw = bool(nchw_out and last and m.out_channels <= 4)
             i += consumed
             if isinstance(after, GDN):

@@ -27,4 +27,11 @@ g++ $CXXFLAGS -I"$INC_PY" -I"$INC_PB" -I"$REF/third_party/ryg_rans" -I"$REF/comp
     "$REF/compressai/cpp_exts/rans/rans_interface.cpp" -o "$OUT/compressai/ans$SUF"
 g++ $CXXFLAGS -I"$INC_PY" -I"$INC_PB" \
     "$REF/compressai/cpp_exts/ops/ops.cpp" -o "$OUT/compressai/_CXX$SUF"
+# The reference's own unit tests of this path, kept beside the install (build output, never tracked) so that
+# tests/test_insitu_gpu.py can run them UNMODIFIED on the GPU box with compressai.ans / compressai._CXX replaced
+# by this repo's modules (plan item 1).
+mkdir -p "$OUT/tests"
+for t in test_entropy_models.py test_ops.py test_coder.py; do
+  cp "$REF/tests/$t" "$OUT/tests/$t"
+done
 echo "build_ref: reference installed in $OUT"

@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 LATENT_RTOL = 1e-3   # max-abs error of y / z relative to max |ref|
-XHAT_ATOL = 2e-3     # max-abs error of reconstructions in [0, 1]
+XHAT_ATOL = 1e-3     # max-abs error of reconstructions in [0, 1] (north_star tolerance, fp32)
 LIK_ATOL = 1e-3      # max-abs error of likelihoods (north_star tolerance, fp32)
 
 
@@ -64,11 +64,35 @@ def test_compress_decompress_vs_reference(golden, orc, name):
     if same_bytes:
         assert np.abs(x_hat - g["x_hat"]).max() <= XHAT_ATOL
     assert np.abs(fwd["x_hat"].clamp(0, 1).cpu().numpy() - x_hat).max() <= XHAT_ATOL
+    # Likelihoods: EVERY element whose quantised symbol agrees with the reference's must be within LIK_ATOL; an
+    # element whose latent sits on a rounding boundary may quantise differently on the GPU (two fp32 conv
+    # implementations differ in the last bits), which moves that element's own likelihood -- those are counted
+    # and bounded, not exempted blindly.  For the hyperprior families a flipped z symbol changes the scales of a
+    # whole neighbourhood of y, so y is compared strictly only when every z symbol agrees.
+    with torch.no_grad():
+        lat = {"y": y.cpu().numpy()}
+        if name != "factorized":
+            lat["z"] = net.h_a(net._hyper_in(y)).cpu().numpy()
+    sd_np = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
+    med = sd_np["entropy_bottleneck.quantiles"][:, 0, 1][None, :, None, None]
+    flips = {}
+    for k in lat:
+        is_eb = (k == "z") or name == "factorized"
+        off = med if is_eb else 0.0
+        if name == "meanscale" and k == "y":
+            flips[k] = None  # means come from h_s(z_hat): handled through the z agreement below
+            continue
+        flips[k] = np.rint(lat[k] - off) != np.rint(g[k] - off)
+    z_agrees = name == "factorized" or not flips["z"].any()
     for k, v in fwd["likelihoods"].items():
         ref = g["fwd_lik_" + k]
-        got = v.cpu().numpy()
-        frac_bad = (np.abs(got - ref) > LIK_ATOL).mean()
-        assert frac_bad <= 0.01, (k, frac_bad)   # a flipped symbol moves its own likelihood
+        err = np.abs(v.cpu().numpy() - ref)
+        f = flips.get(k)
+        if f is not None and (k != "y" or z_agrees):
+            assert f.mean() <= 0.002, (k, f.mean())
+            assert err[~f].max() <= LIK_ATOL, (k, float(err[~f].max()))
+        else:
+            assert (err > LIK_ATOL).mean() <= 0.01, (k, float((err > LIK_ATOL).mean()))
     # coder-boundary parity: oracle coder on OUR symbols / indexes == OUR bytes
     sd = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
     if name == "factorized":
