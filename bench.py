@@ -599,7 +599,7 @@ def ours(args, rank, world):
             else:                    # host tensors straight into the API: micro-batches stream in and out
                 enc = net.compress(x_host)
                 dec = net.decompress(enc["strings"], enc["shape"], out=out_hosts[slot])
-            torch.cuda.current_stream().synchronize()
+            coder.wait_stream()
             nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
             h2d = x_host.numel() * 4 + nbytes
             d2h = nbytes + out_hosts[slot].numel() * 4

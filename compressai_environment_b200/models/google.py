@@ -410,7 +410,7 @@ class ScaleHyperprior(CompressionModel):
         if out is not None and (out.is_cuda or out.dim() != 4 or out.size(0) != n or out.dtype != torch.float32):
             raise ValueError("out must be a float32 CPU tensor [len(strings[0]), 3, H, W]")
         res = self._decompress_chunks(chunks, shape, dev, statuses, out)
-        torch.cuda.current_stream(dev).synchronize()  # one sync per call: surface decoder errors like the reference would
+        coder.wait_stream(torch.cuda.current_stream(dev))  # one (non-spinning) sync per call: surface decoder errors
         coder.check_status(statuses)
         return {"x_hat": res["x_hat"]}
 
