@@ -44,7 +44,9 @@ constexpr int kMaxGdnK = 8;       // GDN k-steps per tile (BN <= 256)
 constexpr int kBK = 32;           // k elements per stage (2 x UMMA_K=16): small stages -> 2 CTAs per SM
 constexpr int kProducerThreads = 64;   // warps 0-1 issue the A-tile cp.async copies (fewer mbarrier arrivals per k-step)
 constexpr int kLoadIters = 8;          // rows per producer thread: kBM / (kProducerThreads / 4)
-constexpr int kConvThreads = 160;
+constexpr int kEpiWarps = 8;             // warps 0-7: two per TMEM lane quarter, taking alternate 32-column slabs
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = kEpiThreads + 32;  // + warp 8: MMA issuer, owns the TMEM allocation
 constexpr int kMaxTaps = 32;
 // A-tile chunk pitch (UMMA leading byte offset): 128 rows x 16 B + 32 B of padding so that a quarter warp that
 // writes 2 pixels x 4 k-chunks touches 8 distinct 16-byte bank groups ((2c + p) mod 8) -> conflict-free LDGSTS
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     for (int g = 0; g < 8; ++g) mbar_init(&gfull_bar[g], 128 + 1);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                  "r"(tmem_cols)
                  : "memory");
@@ -278,23 +280,25 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   const uint32_t tmem_base = s_tmem_base;
   CAI_TRACE(1);
 
-  if (warp == 2 || warp == 3) {
-    // bias / beta of this N tile -> shared memory (warps 2-3 idle through the main loop).  The epilogue reads them
+  if (warp >= 2 && warp < kEpiWarps) {
+    // bias / beta of this N tile -> shared memory (warps 2-7 idle through the main loop).  The epilogue reads them
     // per column group, and a global load there -- L1 is being streamed through by the operand copies -- put an L2
     // round trip on every group (measured: ~40% of the epilogue).  Published by the bar.sync after the acc wait.
-    for (int i = tid - 64; i < BN; i += 64) {
+    for (int i = tid - 64; i < BN; i += kEpiThreads - 64) {
       const bool in = n0 + i < p.Cout;
       s_bias[i] = (p.bias && in) ? __ldg(p.bias + n0 + i) : 0.f;
       s_beta[i] = (fuse_gdn && in) ? __ldg(p.gdn_beta + n0 + i) : 1.f;
     }
   }
-  if (warp < 4) {
+  if (warp < kEpiWarps) {
     // ===================== producers =====================
     // Load mapping: 4 lanes share one pixel (its kBK = 32 channels = 64 contiguous bytes per plane), a warp
     // instruction covers 8 pixels -> 8 L1 wavefronts per LDGSTS instead of 32 with a lane-per-pixel mapping.
     // Thread (warp w, lane l) loads chunk c = l & 3 of rows it * 32 + w * 8 + (l >> 2), it = 0..3.
-    // The epilogue below keeps thread = TMEM lane = row `tid`.
-    const int r = tid;
+    // The epilogue below keeps thread = TMEM lane = row `tid & 127`; the two warps that share a lane quarter
+    // (w and w + 4, group h = tid >> 7) take alternate 32-column slabs of the tile.
+    const int r = tid & (kBM - 1);
+    const int h = tid >> 7;
     const int64_t m = m0 + r;
     const bool row_ok = m < M_total;
     int n_img = 0, pi = 0, pj = 0;
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     // blocking point is the "empty" barrier of the stage being refilled).  Ring positions and parities are carried
     // incrementally.
     int ps = 0, ppass = 0;  // stage of k-step ks, number of completed passes over the ring
-    if (!is_loader) {       // warps 2-3 only take part in the epilogue: fast-forward their ring position
+    if (!is_loader) {       // warps 2-7 only take part in the epilogue: fast-forward their ring position
       ppass = ksteps / stages;
       ps = ksteps - ppass * stages;
     }
@@ -433,37 +437,34 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
     }
     mbar_wait_bounded(&acc_bar, 0);
     tc_fence_after();
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_beta visible to all epilogue warps
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_bias / s_beta visible to all epilogue warps
     CAI_TRACE(3);
-    const uint32_t lane_base = (static_cast<uint32_t>(warp) * 32u) << 16;
+    const uint32_t lane_base = (static_cast<uint32_t>(warp & 3) * 32u) << 16;
     if (fuse_gdn) {
       // ---- fused GDN, part 1: turn the accumulator into the A operand of the second GEMM.
       // x = acc + bias; x^2 is split into bf16 planes and written, kBK channels (one k-step) at a time, into the
       // A area of the next ring stage; gamma's matching K chunk arrives in the B area by TMA.
       // The TMEM load of slab g+1 is in flight while slab g is processed (two register buffers).
-      uint32_t rawbuf[2][32];
-      if (!CAI_DBG(128)) tmem_ld32_nowait(tmem_base + lane_base, rawbuf[0]);
-#pragma unroll
-      for (int g = 0; g < kMaxGdnK; ++g) {
-        if (g >= gdn_ksteps) break;
-        const int s = ps;
-        if (ppass > 0) mbar_wait_bounded(&empty_bar[s], (ppass - 1) & 1);
-        if (++ps == stages) {
-          ps = 0;
-          ++ppass;
+      // Group h writes the k-steps g = h, h + 2, ...: the two groups fill two ring stages concurrently.
+      uint32_t raw[32];
+#pragma unroll 1
+      for (int g = h; g < gdn_ksteps; g += 2) {
+        int s = ps + g, pass = ppass;  // ring stage / pass of GDN k-step g (k-steps continue the main loop's ring walk)
+        while (s >= stages) {
+          s -= stages;
+          ++pass;
         }
+        if (pass > 0) mbar_wait_bounded(&empty_bar[s], (pass - 1) & 1);
         unsigned char *sa = smem + static_cast<uint32_t>(s) * stage_bytes;
-        if (tid == 0 && g >= gdn_pre) {
+        if (r == 0 && g >= gdn_pre) {
           mbar_expect_tx(&gfull_bar[g], 2 * b_plane);
           tma_bulk_g2s(sa + 2 * a_plane, p.gdn_w + static_cast<size_t>(g) * (2 * b_plane), 2 * b_plane, &gfull_bar[g]);
         }
         static_assert(kBK == 32, "the GDN operand phase loads one 32-column TMEM slab per k-step");
-        uint32_t (&raw)[32] = rawbuf[g & 1];
         const int col0 = g * kBK;
         const bool any = col0 < BN;  // warp-uniform (BN is a multiple of 16: a k-step may be half empty)
+        if (any && !CAI_DBG(128)) tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0), raw);
         tmem_wait_ld();
-        if (g + 1 < gdn_ksteps && col0 + kBK < BN && !CAI_DBG(128))
-          tmem_ld32_nowait(tmem_base + lane_base + static_cast<uint32_t>(col0 + kBK), rawbuf[(g + 1) & 1]);
 #pragma unroll
         for (int c = 0; c < kBK / 8; ++c) {
           const int col = col0 + c * 8;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
       const int oy = pi * p.os + p.o0y, ox = pj * p.os + p.o0x;
       opix = (static_cast<int64_t>(n_img) * p.Ho + oy) * p.Wo + ox;
     }
-    s_opix[tid] = opix;
+    if (h == 0) s_opix[r] = opix;
     // staged buffers: fp32 tile and/or bf16 plane pairs (out, out^2, |out|)
     struct StageBuf {
       unsigned char *g;   // global base of the tensor (element (pixel 0, channel 0))
@@ -646,20 +647,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
         }
       };
       {
-        uint32_t qa[16], qa2[16], qb[16], qb2[16];
-        issue(cA, qa, qa2);
-        for (int c0 = cA; c0 < cB; c0 += 32) {
-          tmem_wait_ld();
-          if (c0 + 16 < cB) issue(c0 + 16, qb, qb2);
-          process(c0, qa, qa2);
-          if (c0 + 16 < cB) {
-            tmem_wait_ld();
-            if (c0 + 32 < cB) issue(c0 + 32, qa, qa2);
-            process(c0 + 16, qb, qb2);
+        // group h takes the 32-column slabs h, h + 2, ... of this pass, 16 columns per TMEM load (the other warps
+        // resident on the scheduler -- four epilogue warps per scheduler with two CTAs per SM -- hide the load)
+        uint32_t qa[16], qa2[16];
+#pragma unroll 1
+        for (int s0 = cA + 32 * h; s0 < cB; s0 += 64) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c0 = s0 + 16 * q;
+            if (c0 < cB) {
+              issue(c0, qa, qa2);
+              tmem_wait_ld();
+              process(c0, qa, qa2);
+            }
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (cA == 0) CAI_TRACE(6);
       // ---- phase 2: cooperative copy-out, 16-byte units, consecutive lanes along a row
       const int cols_here = (cB - cA < p.Cout - (n0 + cA)) ? (cB - cA) : (p.Cout - (n0 + cA));
@@ -671,10 +675,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           const uint32_t units = static_cast<uint32_t>(cols_here) * sb.esize / 16u;  // per row
           unsigned char *gbase = sb.g + static_cast<int64_t>(n0 + cA) * sb.esize;
           const int64_t row_stride = static_cast<int64_t>(p.Cout) * sb.esize;
-          if ((units & (units - 1u)) == 0u && units <= 128u) {
+          if ((units & (units - 1u)) == 0u && units <= static_cast<uint32_t>(kEpiThreads)) {
             // power-of-two units per row (the common case): shift / mask indexing, rows_per_iter rows per sweep
             const uint32_t j = tid & (units - 1u);
-            const uint32_t rows_per_iter = 128u / units;
+            const uint32_t rows_per_iter = static_cast<uint32_t>(kEpiThreads) / units;
             uint32_t row = tid / units;  // tid >> log2(units); done once
             const unsigned char *sp = smem + sb.off + row * pitch + j * 16u;
             const uint32_t sp_step = rows_per_iter * pitch;
@@ -685,7 +689,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
             }
           } else {
             const uint32_t total_u = kBM * units;
-            for (uint32_t u = tid; u < total_u; u += 128u) {
+            for (uint32_t u = tid; u < total_u; u += static_cast<uint32_t>(kEpiThreads)) {
               const uint32_t row = u / units, j = u - row * units;
               const int64_t op = s_opix[row];
               if (op < 0) continue;
@@ -695,10 +699,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
   } else {
-    // ===================== MMA issuer (warp 4, one elected lane) =====================
+    // ===================== MMA issuer (warp 8, one elected lane) =====================
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                            (static_cast<uint32_t>(kBM >> 4) << 24);
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_kernel(const __grid
   CAI_TRACE(7);
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }

@@ -36,6 +36,8 @@ _BK = 32
 # Optional profiling hook used by bench.py (same convention as coder.TIMING): when set to a dict, every
 # cai_conv_gemm launch appends a (start, end) CUDA-event pair recorded on the launching stream.
 TIMING = None
+# Same hook with one (label, start, end) record per launch, the label naming the layer shape (tools/layer_times.py).
+DETAIL = None
 
 
 class Conv2d(_cache.CacheOwner, nn.Module):
@@ -341,6 +343,9 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
         if TIMING is not None:
             e1.record()
             TIMING.setdefault("conv_gemm_kernel", []).append((e0, e1))
+            if DETAIL is not None:
+                DETAIL.append((f"gemm {a.C}->{cout} taps={len(taps)} grid={a.N}x{Hp}x{Wp} in={a.H}x{a.W} is={is_} "
+                               f"{'gdn' if gdn is not None else 'epi%d' % epilogue}", e0, e1))
 
 
 _ACT = {None: 0, "relu": 1, "leaky": 2}
