@@ -63,6 +63,7 @@ struct Knobs {
   int coder_warps = 0;      // CAI_CODER_WARPS   (0 = automatic)
   int lut_buckets = 0;      // CAI_LUT_BUCKETS   (0 = automatic)
   int table_smem_kb = -1;   // CAI_TABLE_SMEM_KB (-1 = no cap)
+  int coder_lanes = 0;      // CAI_CODER_LANES   (N > 0: lane-per-string kernels from N strings per launch up; 0 = never, the default)
   int conv_persist = -1;    // CAI_CONV_PERSIST  (-1 = automatic)
   int coder_lut_adapt = -1; // CAI_LUT_ADAPT     (-1 = automatic)
 };
@@ -108,6 +109,10 @@ struct cai_table {
   int in_smem = 0;      // whole blob (with LUT) fits the decoder's shared memory budget
   int enc_in_smem = 0;  // header + meta + cdf fits the encoder's budget
   int device = -1;
+  uint32_t n_cdf_entries = 0;
+  // per-(row, symbol) encoder parameters {reciprocal, bias | shift, freq << 15} for the lane-per-string encoder,
+  // built on first use (rans.cu); 16 bytes per cdf entry, read through L1 / L2 one symbol ahead of the chain
+  void *enc_params = nullptr;
 };
 
 // ---- device-side PTX wrappers ------------------------------------------------------------------------

@@ -548,6 +548,446 @@ rans_decode_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes, 
   }
 }
 
+// ---- lane-per-string kernels -----------------------------------------------------------------------------
+// From 32 strings up, ONE LANE codes one string: the 32 chains of a warp share one instruction stream, so every
+// issued instruction advances 32 strings (the warp-per-string kernels above spend the whole warp's issue slots
+// on one chain, and measurably slow each other down from 4 warps per scheduler on).  The chains still cost their
+// dependent latency per symbol, but a launch of 32 strings now occupies one warp instead of 32, and 4096 strings
+// 128 warps instead of 4096.
+//   * symbols / indexes reach the lanes through warp-transposed staging: per 32-symbol chunk the warp copies, for each
+//     of its 32 strings, 32 consecutive values (one coalesced 128-byte line, cp.async) into a shared-memory tile
+//     with an odd pitch; lane s then walks row s.  Decoded symbols leave through the same transposition.
+//   * everything off the chain is software-pipelined one / two symbols ahead inside a chunk: row metadata (LDS),
+//     then the per-(row, symbol) encoder parameters (one 16-byte read-only load from a table built once per
+//     cai_table: reciprocal, bias | shift, freq << 15 -- the same values the warp kernel derives per symbol).
+//   * each lane owns its output cursor (encoder: words stored backwards from its slot end) or its input cursor
+//     (decoder: next word prefetched into a register when the previous one is consumed).
+constexpr int kTilePitch = 33;
+constexpr int kLaneTileInts = 32 * kTilePitch;
+constexpr int kEncLaneWarpBytes = 2 * 2 * kLaneTileInts * 4 + 32 * 16;  // sym + idx tiles, double buffered; beg / n
+constexpr int kDecLaneWarpBytes = 3 * kLaneTileInts * 4 + 32 * 16;      // idx tiles (x2), output tile; beg / n
+
+__global__ void enc_params_kernel(const unsigned char *__restrict__ blob, uint4 *__restrict__ out) {
+  const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(blob);
+  const RowMeta m = reinterpret_cast<const RowMeta *>(blob + hdr->off_meta)[blockIdx.x];
+  const uint16_t *row = reinterpret_cast<const uint16_t *>(blob + hdr->off_cdf) + m.cdf_off;
+  const int32_t maxv = m.len - 2;
+  for (int32_t v = threadIdx.x; v <= maxv; v += blockDim.x) {
+    const uint32_t c0 = row[v], c1 = row[v + 1];
+    uint32_t freq = (c1 - c0) & 0xFFFFu;
+    if (freq == 0) freq = 1;
+    uint32_t shift = 0, bias = c0;
+    if (freq == 1)
+      bias += 65535u;
+    else
+      shift = 31 - __clz(freq - 1);
+    const uint64_t mm = g_rcp[freq];
+    // the last symbol of a row is the escape symbol: flag it in bit 63 of m (always set in the true value)
+    out[m.cdf_off + v] = make_uint4(static_cast<uint32_t>(mm),
+                                    static_cast<uint32_t>(mm >> 32) & (v == maxv ? 0x7FFFFFFFu : 0xFFFFFFFFu),
+                                    bias | (shift << 20), freq << 15);
+  }
+}
+
+static int ensure_enc_params(cai_table *t, cudaStream_t stream) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (t->enc_params) return CAI_OK;
+  void *p = nullptr;
+  CAI_CUDA(cudaMalloc(&p, sizeof(uint4) * (static_cast<size_t>(t->n_cdf_entries) + 8)));
+  enc_params_kernel<<<t->K, 256, 0, stream>>>(t->blob, static_cast<uint4 *>(p));
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // once per table: visible to every stream afterwards
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("enc_params_kernel failed: %s", cudaGetErrorString(e));
+    return CAI_E_CUDA;
+  }
+  t->enc_params = p;
+  return CAI_OK;
+}
+
+// Copy chunk j (32 values of each of the warp's 32 strings) of `src` into a tile: row s = string wbase + s.
+__device__ __forceinline__ void lane_tile_load(int32_t *tile, const int32_t *__restrict__ src, const int64_t *s_beg,
+                                               const int64_t *s_n, int64_t j, int lane) {
+#pragma unroll 4
+  for (int s2 = 0; s2 < 32; ++s2) {
+    const int64_t i = (j << 5) + lane;
+    int32_t *dst = tile + s2 * kTilePitch + lane;
+    if (i < s_n[s2])
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src + s_beg[s2] + i) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+rans_encode_lanes_kernel(const unsigned char *__restrict__ blob, const uint4 *__restrict__ eparams,
+                         const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
+                         const int64_t *__restrict__ str_begin, int64_t n_per_string, int32_t B,
+                         uint32_t *__restrict__ slots, int64_t slot_words, int32_t *__restrict__ n_words,
+                         int32_t *__restrict__ status, int32_t meta_in_smem) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(blob);
+  const int32_t K = hdr->K;
+  const uint4 *meta = reinterpret_cast<const uint4 *>(blob + hdr->off_meta);
+  uint32_t woff = 0;
+  if (meta_in_smem) {
+    uint4 *sm = reinterpret_cast<uint4 *>(smem);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) sm[k] = __ldg(meta + k);
+    __syncthreads();
+    meta = sm;
+    woff = (static_cast<uint32_t>(K) * 16u + 127u) & ~127u;
+  }
+  unsigned char *wsm = smem + woff + warp * kEncLaneWarpBytes;
+  int32_t *tile_sym = reinterpret_cast<int32_t *>(wsm);                    // [2][kLaneTileInts]
+  int32_t *tile_idx = tile_sym + 2 * kLaneTileInts;                       // [2][kLaneTileInts]
+  int64_t *s_beg = reinterpret_cast<int64_t *>(tile_idx + 2 * kLaneTileInts);  // [32]
+  int64_t *s_n = s_beg + 32;                                              // [32]
+
+  for (int64_t wbase = (static_cast<int64_t>(blockIdx.x) * warps + warp) * 32; wbase < B;
+       wbase += static_cast<int64_t>(gridDim.x) * warps * 32) {
+    const int64_t b = wbase + lane;
+    const bool live = b < B;
+    const int64_t beg = live ? (str_begin ? str_begin[b] : b * n_per_string) : 0;
+    const int64_t n = live ? (str_begin ? (str_begin[b + 1] - beg) : n_per_string) : 0;
+    __syncwarp();
+    s_beg[lane] = beg;
+    s_n[lane] = n;
+    __syncwarp();
+    int64_t nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t other = __shfl_xor_sync(0xffffffffu, nmax, o);
+      nmax = other > nmax ? other : nmax;
+    }
+    const int64_t nchunks = (nmax + 31) >> 5;
+
+    uint64_t x = 1ull << 31;
+    uint32_t cnt = 0;
+    const uint32_t cap = static_cast<uint32_t>(slot_words);
+    uint32_t *outp = slots + (b + 1) * slot_words - 1;  // word k goes to outp[-k]
+    int32_t st = CAI_S_OK;
+    auto push = [&](uint32_t w) {
+      if (cnt < cap) *(outp - cnt) = w;
+      cnt += 1;
+    };
+
+    if (nchunks > 0) {
+      lane_tile_load(tile_sym + ((nchunks - 1) & 1) * kLaneTileInts, symbols, s_beg, s_n, nchunks - 1, lane);
+      lane_tile_load(tile_idx + ((nchunks - 1) & 1) * kLaneTileInts, indexes, s_beg, s_n, nchunks - 1, lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int64_t j = nchunks - 1; j >= 0; --j) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (j >= 1) {  // the other buffer was chunk j + 1's: every lane is done with it
+        lane_tile_load(tile_sym + ((j - 1) & 1) * kLaneTileInts, symbols, s_beg, s_n, j - 1, lane);
+        lane_tile_load(tile_idx + ((j - 1) & 1) * kLaneTileInts, indexes, s_beg, s_n, j - 1, lane);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const int32_t *tsym = tile_sym + (j & 1) * kLaneTileInts + lane * kTilePitch;
+      const int32_t *tidx = tile_idx + (j & 1) * kLaneTileInts + lane * kTilePitch;
+      const int64_t i0 = j << 5;
+
+      // stage M: row metadata of symbol t;  stage A: clamp / escape split + parameter load;  then the chain
+      bool m_ok = false, a_ok = false;
+      int32_t m_sym = 0;
+      uint4 m_meta = make_uint4(0u, 2u, 0u, 0u);
+      uint4 a_e = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t a_raw = 0;
+      auto stage_m = [&](int t) {
+        m_ok = t >= 0 && (i0 + t) < n;
+        int32_t k = 0;
+        m_sym = 0;
+        if (m_ok) {
+          k = tidx[t];
+          m_sym = tsym[t];
+          if (k < 0 || k >= K) {
+            st = CAI_S_BAD_INDEX;
+            k = 0;
+          }
+        }
+        m_meta = meta[k];
+      };
+      auto stage_a = [&]() {
+        a_ok = m_ok;
+        const int32_t maxv = static_cast<int32_t>(m_meta.y) - 2;
+        int32_t v = static_cast<int32_t>(static_cast<uint32_t>(m_sym) - m_meta.z);
+        uint32_t raw = 0;
+        if (v < 0) {
+          raw = static_cast<uint32_t>(-2) * static_cast<uint32_t>(v) - 1u;
+          v = maxv;
+        } else if (v >= maxv) {
+          raw = 2u * static_cast<uint32_t>(v - maxv);
+          v = maxv;
+        }
+        if (maxv < 0) v = 0;  // malformed row: stay in bounds
+        a_raw = raw;
+        a_e = __ldg(eparams + (a_ok ? (m_meta.x + static_cast<uint32_t>(v)) : 0u));
+      };
+      stage_m(31);
+      stage_a();
+      stage_m(30);
+#pragma unroll 2
+      for (int t = 31; t >= 0; --t) {
+        const uint4 e = a_e;
+        const uint32_t raw = a_raw;
+        const bool ok = a_ok;
+        stage_a();
+        stage_m(t - 2);
+        if (ok) {
+          // Rans64EncPut (rans64.h:77-93) with the exact reciprocal; escapes as in the warp kernel above
+          if (!(e.y & 0x80000000u)) {
+            const int nb = raw ? ((35 - __clz(raw)) >> 2) : 0;
+            const uint64_t V = (static_cast<uint64_t>(raw) << 4) | static_cast<uint32_t>(nb);
+            int rem = nb + 1;
+            while (rem > 0) {
+              const int L = 64 - __clzll(x);
+              if (L > 59) {
+                push(static_cast<uint32_t>(x));
+                x >>= 32;
+                continue;
+              }
+              const int J = ((59 - L) >> 2) + 1;
+              const int c = J < rem ? J : rem;
+              const uint64_t part = (V >> (4 * (rem - c))) & ((1ull << (4 * c)) - 1ull);
+              x = (x << (4 * c)) | part;
+              rem -= c;
+            }
+          }
+          const uint32_t xh = static_cast<uint32_t>(x >> 32);
+          if (xh >= e.w) {
+            push(static_cast<uint32_t>(x));
+            x = static_cast<uint64_t>(xh);
+          }
+          const uint64_t m = (static_cast<uint64_t>(e.y | 0x80000000u) << 32) | e.x;
+          const uint32_t shift = e.z >> 20;
+          const uint32_t bias = e.z & 0xFFFFFu;
+          const uint32_t cmpl = 65536u - (e.w >> 15);
+          const uint64_t q = __umul64hi(x, m) >> shift;
+          x = x + bias + q * cmpl;
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (live) {
+      push(static_cast<uint32_t>(x >> 32));
+      push(static_cast<uint32_t>(x));
+      if (cnt > cap) st = CAI_S_OVERFLOW;
+      n_words[b] = static_cast<int32_t>(cnt > cap ? cap : cnt);
+      if (status) status[b] = st;
+    }
+  }
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(256, 1)
+rans_decode_lanes_kernel(const unsigned char *__restrict__ blob, uint32_t blob_bytes,
+                         const uint32_t *__restrict__ words, const int64_t *__restrict__ word_begin,
+                         const int32_t *__restrict__ word_count, const int32_t *__restrict__ indexes,
+                         const int64_t *__restrict__ str_begin, int64_t n_per_string, int32_t B,
+                         int32_t *__restrict__ out, int32_t *__restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bar;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const unsigned char *tbl = blob;
+  uint32_t stage_off = 0;
+  if (kSmem) {
+    stage_blob(smem, blob, blob_bytes, &s_bar);
+    tbl = smem;
+    stage_off = (blob_bytes + 127u) & ~127u;
+  }
+  const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(tbl);
+  const int32_t K = hdr->K;
+  const int lut_shift = hdr->lut_shift;
+  const int32_t nb_row = hdr->lut_buckets;
+  const uint4 *meta = reinterpret_cast<const uint4 *>(tbl + hdr->off_meta);
+  const uint16_t *cdf16 = reinterpret_cast<const uint16_t *>(tbl + hdr->off_cdf);
+  const uint2 *lut = reinterpret_cast<const uint2 *>(tbl + hdr->off_lut);
+
+  unsigned char *wsm = smem + stage_off + warp * kDecLaneWarpBytes;
+  int32_t *tile_idx = reinterpret_cast<int32_t *>(wsm);                      // [2][kLaneTileInts]
+  int32_t *tile_out = tile_idx + 2 * kLaneTileInts;                         // [kLaneTileInts]
+  int64_t *s_beg = reinterpret_cast<int64_t *>(tile_out + kLaneTileInts);   // [32]
+  int64_t *s_n = s_beg + 32;                                                // [32]
+
+  for (int64_t wbase = (static_cast<int64_t>(blockIdx.x) * warps + warp) * 32; wbase < B;
+       wbase += static_cast<int64_t>(gridDim.x) * warps * 32) {
+    const int64_t b = wbase + lane;
+    const bool live = b < B;
+    const int64_t beg = live ? (str_begin ? str_begin[b] : b * n_per_string) : 0;
+    const int64_t n = live ? (str_begin ? (str_begin[b + 1] - beg) : n_per_string) : 0;
+    __syncwarp();
+    s_beg[lane] = beg;
+    s_n[lane] = n;
+    __syncwarp();
+    int64_t nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t other = __shfl_xor_sync(0xffffffffu, nmax, o);
+      nmax = other > nmax ? other : nmax;
+    }
+    const int64_t nchunks = (nmax + 31) >> 5;
+
+    // word feed of this lane's string: the next word sits in a register before the chain needs it
+    const uint32_t *wp = words + (live ? word_begin[b] : 0);
+    const uint32_t nw = live ? static_cast<uint32_t>(word_count ? static_cast<int64_t>(word_count[b])
+                                                                  : (word_begin[b + 1] - word_begin[b]))
+                             : 0u;
+    uint32_t pos = 0;
+    uint32_t nxt = nw > 0 ? __ldg(wp) : 0u;
+    auto take = [&]() -> uint32_t {
+      const uint32_t r = nxt;
+      pos += 1;
+      nxt = pos < nw ? __ldg(wp + pos) : 0u;
+      return r;
+    };
+    uint64_t x;
+    {
+      const uint32_t lo = take();
+      const uint32_t hi = take();
+      x = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+    }
+    int32_t st = CAI_S_OK;
+
+    if (nchunks > 0) lane_tile_load(tile_idx, indexes, s_beg, s_n, 0, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int64_t j = 0; j < nchunks; ++j) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();  // tile j visible; every lane has finished chunk j - 1 (other index buffer, output tile)
+      if (j + 1 < nchunks) lane_tile_load(tile_idx + ((j + 1) & 1) * kLaneTileInts, indexes, s_beg, s_n, j + 1, lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const int32_t *tidx = tile_idx + (j & 1) * kLaneTileInts + lane * kTilePitch;
+      int32_t *tout = tile_out + lane * kTilePitch;
+      const int64_t i0 = j << 5;
+
+      bool d_ok = false;
+      uint4 d_meta = make_uint4(0u, 2u, 0u, 0u);
+      auto stage_d = [&](int t) {
+        d_ok = t < 32 && (i0 + t) < n;
+        int32_t k = 0;
+        if (d_ok) {
+          k = tidx[t];
+          if (k < 0 || k >= K) {
+            st = CAI_S_BAD_INDEX;
+            k = 0;
+          }
+        }
+        d_meta = meta[k];
+      };
+      stage_d(0);
+#pragma unroll 2
+      for (int t = 0; t < 32; ++t) {
+        const uint4 d = d_meta;  // cdf_off, len, offset, lut_off
+        const bool ok = d_ok;
+        stage_d(t + 1);
+        if (ok) {
+          const int32_t maxv = static_cast<int32_t>(d.y) - 2;
+          const uint32_t cf = static_cast<uint32_t>(x) & 0xFFFFu;
+          const uint32_t bk = cf >> lut_shift;
+          const uint2 e = lut[d.w + bk];
+          const uint64_t xn = static_cast<uint64_t>(e.x >> 16) * (x >> 16) + (cf - (e.x & 0xFFFFu));
+          int32_t v = static_cast<int32_t>(e.y);
+          if ((e.x >> 16) != 0u && (xn >> 31) != 0ull) {
+            x = xn;  // one ordinary symbol, no refill
+          } else {
+            uint32_t start = e.x & 0xFFFFu;
+            uint32_t freq = e.x >> 16;
+            int32_t s = static_cast<int32_t>(e.y);
+            if (freq == 0 && (e.y & 0x80000000u)) {
+              s = maxv;  // the whole bucket lies inside the escape symbol
+              start = e.y & 0xFFFFu;
+              freq = 0x10000u - start;
+            } else if (freq == 0) {
+              // bucket spans several symbols: lane-local binary search for the last s in [s, hi] with cdf[s] <= cf;
+              // hi = the symbol holding the next bucket's first value (or the row's last symbol)
+              int32_t hi = maxv;
+              if (static_cast<int32_t>(bk) + 1 < nb_row) {
+                const uint32_t ny = lut[d.w + bk + 1].y;
+                hi = (ny & 0x80000000u) ? maxv : static_cast<int32_t>(ny);
+              }
+              if (hi > maxv) hi = maxv;
+              if (s < 0) s = 0;
+              while (s < hi) {
+                const int32_t mid = (s + hi + 1) >> 1;
+                if (static_cast<uint32_t>(cdf16[d.x + mid]) <= cf)
+                  s = mid;
+                else
+                  hi = mid - 1;
+              }
+              start = cdf16[d.x + s];
+              const uint32_t c_hi = (s >= maxv) ? 0x10000u : static_cast<uint32_t>(cdf16[d.x + s + 1]);
+              freq = c_hi - start;
+              if (freq == 0 || freq > 0x10000u) freq = 1;  // malformed table: keep the chain defined
+            }
+            x = static_cast<uint64_t>(freq) * (x >> 16) + (cf - start);
+            if (x < (1ull << 31)) x = (x << 32) | take();
+            v = s;
+            if (s == maxv) {
+              // bypass / escape decoding (rans_interface.cpp:256-278), grouped nibble pops as in the warp kernel
+              uint32_t raw;
+              const uint32_t t0 = static_cast<uint32_t>(x) & 15u;
+              const int js0 = (64 - __clzll(x) - 28) >> 2;
+              if (t0 < 15u && static_cast<int>(t0) + 1 <= js0) {
+                raw = static_cast<uint32_t>((x >> 4) & ((1ull << (4u * t0)) - 1ull));
+                x >>= 4u * (t0 + 1u);
+                if (static_cast<int>(t0) + 1 == js0) x = (x << 32) | take();
+              } else {
+                uint32_t tt = static_cast<uint32_t>(x) & 15u;
+                x >>= 4;
+                if (x < (1ull << 31)) x = (x << 32) | take();
+                int32_t nb = static_cast<int32_t>(tt);
+                while (tt == 15u) {
+                  tt = static_cast<uint32_t>(x) & 15u;
+                  x >>= 4;
+                  if (x < (1ull << 31)) x = (x << 32) | take();
+                  nb += static_cast<int32_t>(tt);
+                }
+                uint64_t acc = 0;
+                int done = 0;
+                int rem = nb;
+                while (rem > 0) {
+                  const int L = 64 - __clzll(x);
+                  int js = (L - 31 + 3) >> 2;
+                  if (js < 1) js = 1;  // only reachable on corrupt / truncated streams (x < 2^31)
+                  const int c = rem < js ? rem : js;
+                  const uint64_t bits = x & ((1ull << (4 * c)) - 1ull);
+                  x >>= 4 * c;
+                  if (done < 8) acc |= bits << (4 * done);
+                  done += c;
+                  rem -= c;
+                  if (c == js) x = (x << 32) | take();
+                }
+                raw = static_cast<uint32_t>(acc);
+              }
+              const int32_t sraw = static_cast<int32_t>(raw);
+              v = sraw >> 1;
+              v = (sraw & 1) ? (-v - 1) : (v + maxv);
+            }
+          }
+          tout[t] = v + static_cast<int32_t>(d.z);
+        }
+      }
+      __syncwarp();
+      // transposed store: row s2 of the output tile = 32 consecutive symbols of string wbase + s2
+#pragma unroll 4
+      for (int s2 = 0; s2 < 32; ++s2) {
+        const int64_t i = i0 + lane;
+        if (i < s_n[s2]) out[s_beg[s2] + i] = tile_out[s2 * kTilePitch + lane];
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (live) {
+      if (pos > nw) st = st ? st : CAI_S_TRUNCATED;
+      if (status) status[b] = st;
+    }
+  }
+}
+
 // ---- compaction ----------------------------------------------------------------------------------------
 __global__ void scan_words_kernel(const int32_t *__restrict__ n_words, int32_t B, int64_t *__restrict__ out_begin) {
   __shared__ int64_t s_scan[1024];
@@ -618,6 +1058,30 @@ static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
   return 0;
 }
 
+// Lane-per-string kernels from CAI_CODER_LANES strings per launch up; off by default.  Measured on B200 (r2):
+// bit-exact, and a launch of 32 strings occupies one warp instead of 32 -- but every instruction of the per-symbol
+// step (~115 warp instructions with the divergent refill / search / escape paths serialised) now sits on ONE
+// in-order issue stream at ~5 cycles apiece, so a step costs 600-800 cycles against 160-250 cycles per symbol of
+// the warp-per-string kernels whose off-chain work is spread over 32 lanes: C3 9.2 / 5.5 vs 18.3 / 15.4 Gsym/s.
+static bool use_lanes(int32_t B) {
+  const int k = knobs().coder_lanes;
+  return k > 0 && B >= k;
+}
+
+// 32 strings per warp; as many CTAs as there are SMs before a CTA gets a second warp (chains are latency bound:
+// spreading the warps buys more than packing them), at most `max_warps` warps per CTA, persistent beyond that.
+static void plan_lanes(const DeviceProps &dp, int32_t B, int max_warps, int *warps, int *grid) {
+  const int nw = (B + 31) / 32;
+  int w = (nw + dp.sm_count - 1) / dp.sm_count;
+  if (w > max_warps) w = max_warps;
+  if (w < 1) w = 1;
+  int g = (nw + w - 1) / w;
+  const int cap = dp.sm_count * 4;
+  if (g > cap) g = cap;
+  *warps = w;
+  *grid = g < 1 ? 1 : g;
+}
+
 int cai_rans_encode_batch(cai_table_t t, const int32_t *symbols, const int32_t *indexes,
                           const int64_t *str_begin, int64_t n_per_string, int32_t B, uint32_t *slots,
                           int64_t slot_words, int32_t *n_words, int32_t *status, cai_stream_t stream_) {
@@ -636,6 +1100,25 @@ int cai_rans_encode_batch(cai_table_t t, const int32_t *symbols, const int32_t *
   rc = ensure_rcp_table(dp.device);
   if (rc != CAI_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (use_lanes(B)) {
+    // lane-per-string: 32 strings per warp (see the kernel comment); tables are read through L1 / L2 off the chain
+    rc = ensure_enc_params(t, stream);
+    if (rc != CAI_OK) return rc;
+    int lw, lgrid;
+    plan_lanes(dp, B, 8, &lw, &lgrid);
+    const int meta_in_smem = static_cast<size_t>(t->K) * 16 <= 32 * 1024;
+    const size_t smem = (meta_in_smem ? ((static_cast<size_t>(t->K) * 16 + 127) & ~static_cast<size_t>(127)) : 0) +
+                        static_cast<size_t>(lw) * kEncLaneWarpBytes;
+    int max_dyn = 0;
+    rc = optin_max_smem(reinterpret_cast<const void *>(rans_encode_lanes_kernel), dp, &max_dyn);
+    if (rc != CAI_OK) return rc;
+    CAI_CHECK_ARG(smem <= static_cast<size_t>(max_dyn), "cai_rans_encode_batch: staging does not fit shared memory");
+    rans_encode_lanes_kernel<<<lgrid, lw * 32, smem, stream>>>(t->blob, static_cast<const uint4 *>(t->enc_params),
+                                                              symbols, indexes, str_begin, n_per_string, B, slots,
+                                                              slot_words, n_words, status, meta_in_smem);
+    CAI_LAUNCH_CHECK();
+    return CAI_OK;
+  }
   int warps, grid;
   plan_grid(dp, B, &warps, &grid);
   if (t->enc_in_smem) {
@@ -693,9 +1176,31 @@ int cai_rans_decode_batch(cai_table_t t, const uint32_t *words, const int64_t *w
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const uint32_t bytes = static_cast<uint32_t>(t->blob_bytes);
+  if (use_lanes(B) && !state) {
+    int max_dyn = 0;
+    const void *fn = t->in_smem ? reinterpret_cast<const void *>(rans_decode_lanes_kernel<true>)
+                                : reinterpret_cast<const void *>(rans_decode_lanes_kernel<false>);
+    rc = optin_max_smem(fn, dp, &max_dyn);
+    if (rc != CAI_OK) return rc;
+    const size_t base = t->in_smem ? ((bytes + 127u) & ~127u) : 0;
+    int fit = static_cast<int>((static_cast<size_t>(max_dyn) - base) / kDecLaneWarpBytes);
+    CAI_CHECK_ARG(static_cast<size_t>(max_dyn) > base && fit >= 1, "cai_rans_decode_batch: table does not fit shared memory");
+    int lw, lgrid;
+    plan_lanes(dp, B, fit < 8 ? fit : 8, &lw, &lgrid);
+    if (t->in_smem && lgrid > dp.sm_count) lgrid = dp.sm_count;  // one CTA per SM: each stages the table
+    const size_t smem = base + static_cast<size_t>(lw) * kDecLaneWarpBytes;
+    if (t->in_smem)
+      rans_decode_lanes_kernel<true><<<lgrid, lw * 32, smem, stream>>>(t->blob, bytes, words, word_begin, word_count,
+                                                                      indexes, str_begin, n_per_string, B, out, status);
+    else
+      rans_decode_lanes_kernel<false><<<lgrid, lw * 32, smem, stream>>>(t->blob, bytes, words, word_begin, word_count,
+                                                                       indexes, str_begin, n_per_string, B, out, status);
+    CAI_LAUNCH_CHECK();
+    return CAI_OK;
+  }
   int warps, grid;
   plan_grid(dp, B, &warps, &grid);
-  const uint32_t bytes = static_cast<uint32_t>(t->blob_bytes);
   if (t->in_smem) {
     const size_t smem = ((bytes + 127u) & ~127u) + static_cast<size_t>(warps) * kDecWarpBytes;
     int max_dyn = 0;

@@ -89,6 +89,7 @@ const Knobs &knobs() {
     r.coder_warps = env_int("CAI_CODER_WARPS", 0);
     r.lut_buckets = env_int("CAI_LUT_BUCKETS", 0);
     r.table_smem_kb = env_int("CAI_TABLE_SMEM_KB", -1);
+    r.coder_lanes = env_int("CAI_CODER_LANES", 0);
     r.conv_persist = env_int("CAI_CONV_PERSIST", -1);
     r.coder_lut_adapt = env_int("CAI_LUT_ADAPT", -1);
     return r;
@@ -286,6 +287,7 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
     return CAI_E_CUDA;
   }
   t->blob_bytes = h.total_bytes;
+  t->n_cdf_entries = h.n_cdf_entries;
   t->enc_bytes = h.enc_bytes;
   t->K = K;
   t->Lmax = Lmax;
@@ -305,6 +307,7 @@ int cai_table_create(const int32_t *cdfs, const int32_t *cdf_len, const int32_t 
 void cai_table_destroy(cai_table_t t) {
   if (!t) return;
   if (t->blob) cudaFree(t->blob);
+  if (t->enc_params) cudaFree(t->enc_params);
   delete t;
 }
 

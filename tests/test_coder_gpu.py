@@ -274,3 +274,80 @@ def test_eb_quantize_index(orc, layout):
     out = kernels.dequantize(sym, None, torch.from_numpy(med).to(dev), shape, mf)
     assert np.array_equal(out.cpu().numpy(),
                           orc.dequantize(orc.quantize_symbols(x, med[None, :, None, None]), med[None, :, None, None]))
+
+
+@pytest.mark.parametrize("B", [32, 40, 97])
+def test_lane_per_string_ragged_vs_oracle(golden, orc, gc_table, B):
+    """The lane-per-string kernels (32 strings per warp, used from 32 strings per launch up) through the raw C ABI
+    with RAGGED strings (``str_begin``): lengths 0 .. ~2000 incl. empty strings, chunk-boundary lengths (31, 32, 33,
+    64), every table row, escapes on both sides (symbols far outside the rows), all compared with the oracle byte
+    for byte and decoded back exactly."""
+    from compressai_environment_b200 import _lib
+    from compressai_environment_b200._lib import check, current_stream, lib, ptr
+
+    c = golden("cdf")
+    rng = np.random.default_rng(B)
+    lens = rng.integers(0, 2000, B)
+    lens[:6] = [0, 31, 32, 33, 64, 1]
+    begin = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=begin[1:])
+    total = int(begin[-1])
+    idx = rng.integers(0, 64, total).astype(np.int32)
+    sym = np.rint(rng.standard_normal(total) * c["gc_scale_table"][idx] * rng.choice([0.3, 1.0, 6.0], total)).astype(np.int32)
+    sym[rng.integers(0, total, 50)] = rng.integers(-2_000_000, 2_000_000, 50)  # long escapes (up to 6 payload nibbles)
+    dev = torch.device("cuda")
+    d_sym, d_idx, d_beg = (torch.from_numpy(a).to(dev) for a in (sym, idx, begin))
+    sw = int(lib().cai_rans_slot_words(int(lens.max())))
+    slots = torch.zeros((B, sw), dtype=torch.int32, device=dev)
+    n_words = torch.zeros(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    check(lib().cai_rans_encode_batch(gc_table.handle, ptr(d_sym), ptr(d_idx), ptr(d_beg), 0, B, ptr(slots), sw,
+                                      ptr(n_words), ptr(status), current_stream()), "cai_rans_encode_batch")
+    torch.cuda.synchronize()
+    assert int(status.abs().max()) == 0
+    nw = n_words.cpu().numpy()
+    sl = slots.cpu().numpy().view(np.uint32)
+    for b in range(B):
+        ours = sl[b, sw - nw[b]:].tobytes()
+        ref = orc.rans_encode(sym[begin[b]:begin[b + 1]], idx[begin[b]:begin[b + 1]], c["gc_cdf"], c["gc_len"], c["gc_off"])
+        assert ours == ref, (b, int(lens[b]))
+    # decode in place from the slots (word_begin = end of slot - n_words, word_count = n_words)
+    wb = (torch.arange(1, B + 1, device=dev, dtype=torch.int64) * sw) - n_words.to(torch.int64)
+    out = torch.full((max(total, 1),), -7, dtype=torch.int32, device=dev)
+    dstat = torch.zeros(B, dtype=torch.int32, device=dev)
+    check(lib().cai_rans_decode_batch(gc_table.handle, ptr(slots), ptr(wb), ptr(n_words), ptr(d_idx), ptr(d_beg), 0, B,
+                                      ptr(out), None, 0, ptr(dstat), current_stream()), "cai_rans_decode_batch")
+    torch.cuda.synchronize()
+    assert int(dstat.abs().max()) == 0
+    assert np.array_equal(out.cpu().numpy()[:total], sym)
+    # a truncated string is reported (status 6), a bad index too (status 2), without disturbing the other strings
+    nw_cut = n_words.clone()
+    victim = int(np.argmax(lens))
+    nw_cut[victim] = max(1, int(nw[victim]) // 2)
+    wb_cut = wb.clone()
+    check(lib().cai_rans_decode_batch(gc_table.handle, ptr(slots), ptr(wb_cut), ptr(nw_cut), ptr(d_idx), ptr(d_beg), 0, B,
+                                      ptr(out), None, 0, ptr(dstat), current_stream()), "cai_rans_decode_batch")
+    torch.cuda.synchronize()
+    ds = dstat.cpu().numpy()
+    assert ds[victim] == 6 and (np.delete(ds, victim) == 0).all()
+    bad = d_idx.clone()
+    bad[int(begin[victim])] = 64
+    check(lib().cai_rans_encode_batch(gc_table.handle, ptr(d_sym), ptr(bad), ptr(d_beg), 0, B, ptr(slots), sw,
+                                      ptr(n_words), ptr(status), current_stream()), "cai_rans_encode_batch")
+    torch.cuda.synchronize()
+    es = status.cpu().numpy()
+    assert es[victim] == 2 and (np.delete(es, victim) == 0).all()
+
+
+def test_lane_per_string_kernels_enabled():
+    """The same ragged / oracle test with the lane-per-string kernels switched on (CAI_CODER_LANES is read once per
+    process, hence the subprocess).  They are off by default (slower, see rans.cu) but must stay bit-exact."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, CAI_CODER_LANES="32")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p",
+                          "no:cacheprovider", "-k", "test_lane_per_string_ragged_vs_oracle"], capture_output=True,
+                         text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "3 passed" in out.stdout, out.stdout[-2000:] + out.stderr[-1000:]
