@@ -39,7 +39,7 @@ class ConvDesc(Structure):
                 + [(n, c_int32) for n in ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "Hp", "Wp", "os", "o0y", "o0x", "is_",
                                           "ntaps", "BN", "epilogue")]
                 + [("clamp_lo", c_float), ("clamp_hi", c_float), ("dy", c_int8 * 32), ("dx", c_int8 * 32), ("glen", c_int8 * 32),
-                   ("gdn_w", c_void_p), ("gdn_beta", c_void_p), ("gdn_mode", c_int32)])
+                   ("gdn_w", c_void_p), ("gdn_beta", c_void_p), ("gdn_mode", c_int32), ("mode", c_int32)])
 
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/cai_b200.h
@@ -75,6 +75,7 @@ SIGNATURES = {
     "cai_eb_logits": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_int64, c_int64, c_void_p,
                               c_void_p, c_void_p]),
     "cai_conv_gemm": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "cai_conv_tma_eligible": (c_int, [POINTER(ConvDesc)]),
     "cai_split_planes": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cai_im2col_split": (c_int, [c_void_p] + [c_int32] * 11 + [c_void_p, c_void_p, c_void_p]),
     "cai_col2im": (c_int, [c_void_p, c_void_p] + [c_int32] * 11 + [c_float, c_float, c_void_p, c_void_p]),
@@ -109,7 +110,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)  # AttributeError here = header / library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if L.cai_abi_version() != 1:
+        if L.cai_abi_version() != 2:
             raise CaiError("libcai_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -195,10 +195,12 @@ def _grouped(taps, rows, step: int):
     return out, [rows[i] for i in order]
 
 
-def pack_weights(w_taps: Tensor, bn: int, glen=None) -> Tensor:
+def pack_weights(w_taps: Tensor, bn: int, glen=None, order: str = "group") -> Tensor:
     """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][k-step][hi | lo][BN x 32 bf16] in the UMMA canonical
     K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2).
-    k-step order: for tap group (``glen``, default one tap per group): for channel chunk: for tap in group."""
+    k-step order ``"group"`` (per-tile kernel, conv.cu): for tap group (``glen``, default one tap per group): for
+    channel chunk: for tap in group.  ``"chunk"`` (persistent TMA kernel, conv_tma.cu): for channel chunk: for tap
+    (taps already sorted by group)."""
     T, cout, cin = w_taps.shape
     nt = (cout + bn - 1) // bn
     kc = (cin + _BK - 1) // _BK
@@ -208,7 +210,10 @@ def pack_weights(w_taps: Tensor, bn: int, glen=None) -> Tensor:
     hi = wp.to(torch.bfloat16)
     lo = (wp - hi.float()).to(torch.bfloat16)
     packed = torch.stack([hi, lo], dim=3)  # nt, T, kc, 2, k8, r8, r%8, k%8
-    if glen is not None and any(g > 1 for g in glen):
+    if order == "chunk":
+        if T > 1 and kc > 1:
+            packed = packed.transpose(1, 2)  # nt, kc, T, ...
+    elif glen is not None and any(g > 1 for g in glen):
         assert sum(glen) == T
         sched, t0 = [], 0
         for g in glen:
@@ -222,9 +227,11 @@ def pack_weights(w_taps: Tensor, bn: int, glen=None) -> Tensor:
 class _Layer:
     """One GEMM launch family prepared from a module (cached on the module, keyed by parameter versions)."""
 
-    def __init__(self, kind, packed, bias, taps_per_phase, bn, cin, cout, geom):
+    def __init__(self, kind, packed, bias, taps_per_phase, bn, cin, cout, geom, packed_c=None):
         self.kind, self.packed, self.bias, self.phases, self.bn = kind, packed, bias, taps_per_phase, bn
         self.cin, self.cout, self.geom = cin, cout, geom
+        # the same weights with k-steps in the persistent TMA kernel's order (None: identical to `packed`)
+        self.packed_c = packed_c if packed_c is not None else packed
 
 
 def _prep_conv(m: "Conv2d") -> _Layer:
@@ -251,8 +258,9 @@ def _build_conv(m: "Conv2d") -> _Layer:
         wt = torch.stack(rows, 0)
         cp, kp = _c16(cout), _c16(cin)
         bn = _choose_bn(cp)
-        lay = _Layer("conv", pack_weights(_pad_taps(wt, cp, kp), bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
-                     (k, s, p))
+        wpad = _pad_taps(wt, cp, kp)
+        lay = _Layer("conv", pack_weights(wpad, bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
+                     (k, s, p), packed_c=pack_weights(wpad, bn, taps.glen, order="chunk"))
     return lay
 
 
@@ -273,7 +281,7 @@ def _build_deconv(m: "ConvTranspose2d") -> _Layer:
     else:
         cp, kp = _c16(cout), _c16(cin)
         bn = _choose_bn(cp)
-        phases, blobs = [], []
+        phases, blobs, blobs_c = [], [], []
         for py in range(s):
             for px in range(s):
                 taps, ws = [], []
@@ -288,8 +296,10 @@ def _build_deconv(m: "ConvTranspose2d") -> _Layer:
                 if ws:
                     taps, ws = _grouped(taps, ws, 1)
                 phases.append(taps)
-                blobs.append(pack_weights(_pad_taps(torch.stack(ws, 0), cp, kp), bn, taps.glen) if ws else None)
-        lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op))
+                wpad = _pad_taps(torch.stack(ws, 0), cp, kp) if ws else None
+                blobs.append(pack_weights(wpad, bn, taps.glen) if ws else None)
+                blobs_c.append(pack_weights(wpad, bn, taps.glen, order="chunk") if ws else None)
+        lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op), packed_c=blobs_c)
     return lay
 
 
@@ -311,7 +321,7 @@ def _build_gdn(m) -> _Layer:
 
 # ---- launches -------------------------------------------------------------------------------------------------
 def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o0x, is_, epilogue=0, aux: Planes = None,
-            out_f32=None, out: Planes = None, sq: Planes = None, ab: Planes = None, clamp=None, gdn=None):
+            out_f32=None, out: Planes = None, sq: Planes = None, ab: Planes = None, clamp=None, gdn=None, packed_c=None):
     d = ConvDesc()
     if gdn is not None:  # fused GDN / IGDN: (packed gamma, beta, mode)
         d.gdn_w, d.gdn_beta, d.gdn_mode = gdn[0].data_ptr(), gdn[1].data_ptr(), gdn[2]
@@ -336,6 +346,9 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
     for g, n in enumerate(getattr(taps, "glen", None) or [1] * len(taps)):
         d.glen[g] = n
     with torch.cuda.device(a.hi.device):
+        # the wide layers go to the persistent TMA-fed kernel (its own k-step order of the same weights)
+        if packed_c is not None and aux is None and sq is None and lib().cai_conv_tma_eligible(d):
+            d.w_packed, d.mode = packed_c.data_ptr(), 1
         if TIMING is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -345,7 +358,7 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
             TIMING.setdefault("conv_gemm_kernel", []).append((e0, e1))
             if DETAIL is not None:
                 DETAIL.append((f"gemm {a.C}->{cout} taps={len(taps)} grid={a.N}x{Hp}x{Wp} in={a.H}x{a.W} is={is_} "
-                               f"{'gdn' if gdn is not None else 'epi%d' % epilogue}", e0, e1))
+                               f"{'gdn' if gdn is not None else 'epi%d' % epilogue}{' tma' if d.mode else ''}", e0, e1))
 
 
 _ACT = {None: 0, "relu": 1, "leaky": 2}
@@ -382,7 +395,7 @@ def _run_conv(m, x, act, want, clamp=None, gdn=None):
                                          current_stream()), "cai_im2col_split")
         o = _outputs(N, Ho, Wo, lay.cout, dev, want)
         _launch(a, lay.packed, lay.bias, [(0, 0)], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, 1, _ACT[act], None, *o,
-                clamp=clamp, gdn=gdn)
+                clamp=clamp, gdn=gdn, packed_c=lay.packed_c)
         return o
     if not isinstance(x, Planes):
         x = to_planes(x, lay.cin)
@@ -390,7 +403,7 @@ def _run_conv(m, x, act, want, clamp=None, gdn=None):
     Ho, Wo = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
     o = _outputs(x.N, Ho, Wo, lay.cout, dev, want)
     _launch(x, lay.packed, lay.bias, lay.phases[0], lay.bn, lay.cout, Ho, Wo, Ho, Wo, 1, 0, 0, s, _ACT[act], None, *o,
-            clamp=clamp, gdn=gdn)
+            clamp=clamp, gdn=gdn, packed_c=lay.packed_c)
     return o
 
 
@@ -404,7 +417,7 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None, 
         Ho, Wo = (x.H - 1) * s - 2 * p + k + op, (x.W - 1) * s - 2 * p + k + op
         cols = torch.empty((x.N, x.H, x.W, npad), dtype=torch.float32, device=dev)
         _launch(x, lay.packed, None, [(0, 0)], lay.bn, npad, x.H, x.W, x.H, x.W, 1, 0, 0, 1, 0, None, cols, None, None,
-                None)
+                None, packed_c=lay.packed_c)
         if final_layout_nchw:
             if dst is not None:  # caller-provided destination (a contiguous slice of a batch tensor)
                 if tuple(dst.shape) != (x.N, lay.cout, Ho, Wo) or not dst.is_contiguous() or dst.dtype != torch.float32:
@@ -429,7 +442,7 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None, 
     i = 0
     for py in range(s):
         for px in range(s):
-            taps, blob = lay.phases[i], lay.packed[i]
+            taps, blob, blob_c = lay.phases[i], lay.packed[i], lay.packed_c[i]
             i += 1
             Hp, Wp = (Ho - py + s - 1) // s, (Wo - px + s - 1) // s
             if Hp <= 0 or Wp <= 0:
@@ -437,7 +450,7 @@ def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None, 
             if not taps:
                 raise _lib.CaiError("transposed convolution phase without taps is not supported (kernel < stride)")
             _launch(x, blob, lay.bias, taps, lay.bn, lay.cout, Ho, Wo, Hp, Wp, s, py, px, 1, _ACT[act], None, *o,
-                    clamp=clamp, gdn=gdn)
+                    clamp=clamp, gdn=gdn, packed_c=blob_c)
     return o
 
 

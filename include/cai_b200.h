@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define CAI_ABI_VERSION 1
+#define CAI_ABI_VERSION 2
 
 /* host-side error codes */
 #define CAI_OK 0
@@ -259,9 +259,18 @@ typedef struct cai_conv_desc {
   const void *gdn_w;
   const float *gdn_beta;
   int32_t gdn_mode;
+  /* 0: per-tile kernel, w_packed k-steps ordered tap group -> channel chunk -> tap (conv.cu).
+   * 1: persistent TMA-fed kernel (conv_tma.cu), w_packed k-steps ordered channel chunk -> tap group -> tap; only
+   *    valid when cai_conv_tma_eligible() accepts the same descriptor. */
+  int32_t mode;
 } cai_conv_desc;
 
 int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream);
+
+/* 1 if the persistent TMA-fed kernel takes this layer (row-segment tiles of a grid at least 64 pixels wide, all output
+ * channels in one tile of at most 128, input stride 1 or 2, grouped taps, 16-byte aligned planes), else 0.  The caller
+ * then packs the weights in the order of mode 1 and sets d->mode = 1. */
+int cai_conv_tma_eligible(const cai_conv_desc *d);
 
 /* fp32 latent / image (layout NCHW or NHWC) -> split planes [N, HW, Cpad] (channels zero padded to Cpad) */
 int cai_split_planes(const float *x, int32_t layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad, void *hi, void *lo,

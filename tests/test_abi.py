@@ -27,7 +27,7 @@ def test_library_exports_header():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in cai_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms
-    assert _lib.lib().cai_abi_version() == 1
+    assert _lib.lib().cai_abi_version() == 2
 
 
 def test_slot_words_bound():
