@@ -21,6 +21,7 @@ on the hot path named by BASELINE.json and is delegated to torch autograd (libra
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -38,6 +39,10 @@ _BK = 32
 TIMING = None
 # Same hook with one (label, start, end) record per launch, the label naming the layer shape (tools/layer_times.py).
 DETAIL = None
+# Which eligible layers go to the persistent TMA-fed kernel (conv_tma.cu): "auto" = where it measures faster than
+# the per-tile kernel on B200 (single-tap GEMMs: the K = 80 first layer and the last-layer GEMM, whose tiles are
+# epilogue-bound), "all" = every layer cai_conv_tma_eligible() accepts (tests, experiments), "none".
+TMA_POLICY = os.environ.get("CAI_TMA_POLICY", "auto")
 
 
 class Conv2d(_cache.CacheOwner, nn.Module):
@@ -347,7 +352,8 @@ def _launch(a: Planes, packed, bias, taps, bn, cout, Ho, Wo, Hp, Wp, os_, o0y, o
         d.glen[g] = n
     with torch.cuda.device(a.hi.device):
         # the wide layers go to the persistent TMA-fed kernel (its own k-step order of the same weights)
-        if packed_c is not None and aux is None and sq is None and lib().cai_conv_tma_eligible(d):
+        want_tma = TMA_POLICY == "all" or (TMA_POLICY == "auto" and len(taps) == 1)
+        if want_tma and packed_c is not None and aux is None and sq is None and lib().cai_conv_tma_eligible(d):
             d.w_packed, d.mode = packed_c.data_ptr(), 1
         if TIMING is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -24,12 +24,13 @@ def _run(mods, x, expect_tma, **kw):
     from compressai_environment_b200 import transforms as T
 
     T.TIMING, T.DETAIL = {}, []
+    policy, T.TMA_POLICY = T.TMA_POLICY, "all"
     try:
         out = T.run_stack(mods, x, **kw)
         torch.cuda.synchronize()
         labels = [d[0] for d in T.DETAIL]
     finally:
-        T.TIMING, T.DETAIL = None, None
+        T.TIMING, T.DETAIL, T.TMA_POLICY = None, None, policy
     n_tma = sum(lbl.endswith(" tma") for lbl in labels)
     assert n_tma == expect_tma, labels
     return out
