@@ -460,6 +460,20 @@ def parity_gate(net, x_dev, x_host, mb, n_oracle=4):
                                                    + sum(int(a != b) for a, b in zip(enc_h["strings"][1], dev_z))
                                                    + abs(len(dev_y) - len(enc_h["strings"][0])))
         rep["host_vs_device_x_hat_max_abs"] = float((dec_h["x_hat"].to(x_hat_dev.device) - x_hat_dev).abs().max())
+        # 8-bit host buffers (the e2e_u8 leg): compress(uint8) == compress(uint8 / 255.0) byte for byte, and the
+        # uint8 reconstruction == round(x_hat * 255) of the float path
+        nq = min(mb, B)
+        xq = (x_host[:nq] * 255.0).round().to(torch.uint8).pin_memory()
+        enc_q = net.compress(xq)
+        enc_f = net.compress((xq.float() / 255.0).pin_memory())
+        out_q = torch.empty((nq, 3, H, W), dtype=torch.uint8).pin_memory()
+        out_f = torch.empty((nq, 3, H, W), dtype=torch.float32).pin_memory()
+        net.decompress(enc_q["strings"], enc_q["shape"], out=out_q)
+        net.decompress(enc_f["strings"], enc_f["shape"], out=out_f)
+        torch.cuda.synchronize()
+        rep["u8_vs_float_strings_differing"] = sum(int(a != b) for k in (0, 1)
+                                                   for a, b in zip(enc_q["strings"][k], enc_f["strings"][k]))
+        rep["u8_vs_float_pixels_differing"] = int((out_q != (out_f * 255.0).round().to(torch.uint8)).sum())
         # floating point yardstick: torch fp32 synthesis of the first images' decoded latents
         nb = min(2, B)
         y_sym0 = net._analysis_chunk(x_dev[:mb])[0][:nb].contiguous()
@@ -475,6 +489,7 @@ def parity_gate(net, x_dev, x_host, mb, n_oracle=4):
                                             and float(x_hat_dev.max()) <= 1.0)
     rep["ok"] = (rep["device_path_statuses_nonzero"] == 0 and n_sym_bad == 0 and bad_bytes == 0
                  and rep["host_vs_device_strings_differing"] == 0 and rep["host_vs_device_x_hat_max_abs"] == 0.0
+                 and rep["u8_vs_float_strings_differing"] == 0 and rep["u8_vs_float_pixels_differing"] == 0
                  and rep["x_hat_vs_fp64_max_abs"] <= rep["x_hat_tolerance"] and rep["x_hat_finite_in_range"])
     return rep
 
@@ -578,6 +593,10 @@ def ours(args, rank, world):
         free_slots.put(i)
     host_cpu_s = []
 
+    e2e_mode = {"u8": False}
+    x_host_u8 = (x_host * 255.0).round().to(torch.uint8).pin_memory()   # the same images as 8-bit pixels
+    out_hosts_u8 = [torch.empty((B, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(n_e2e_workers)]
+
     def step_e2e(_=0):
         """One request through the PUBLIC API with host buffers: pinned images -> H2D -> model.compress() (strings on
         the host) -> model.decompress(strings) -> reconstruction copied to a caller-provided pinned buffer."""
@@ -596,13 +615,17 @@ def ours(args, rank, world):
                 enc = net.compress(xb)
                 dec = net.decompress(enc["strings"], enc["shape"])
                 out_hosts[slot].copy_(dec["x_hat"], non_blocking=True)
+            elif e2e_mode["u8"]:     # 8-bit pixels over PCIe, x / 255 and round(x_hat * 255) on the device
+                enc = net.compress(x_host_u8)
+                dec = net.decompress(enc["strings"], enc["shape"], out=out_hosts_u8[slot])
             else:                    # host tensors straight into the API: micro-batches stream in and out
                 enc = net.compress(x_host)
                 dec = net.decompress(enc["strings"], enc["shape"], out=out_hosts[slot])
             coder.wait_stream()
             nbytes = sum(len(s) for lst in enc["strings"] for s in lst)
-            h2d = x_host.numel() * 4 + nbytes
-            d2h = nbytes + out_hosts[slot].numel() * 4
+            esz = 1 if e2e_mode["u8"] else 4
+            h2d = x_host.numel() * esz + nbytes
+            d2h = nbytes + out_hosts[slot].numel() * esz
         host_cpu_s.append(time.thread_time() - c0)
         return h2d, d2h, nbytes
 
@@ -697,6 +720,16 @@ def ours(args, rank, world):
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
         e2e_host_cpu = sum(host_cpu_s) / max(1, len(host_cpu_s))
         barrier()
+        # the same loop with 8-bit host buffers (uint8 images in, uint8 reconstruction out)
+        e2e_mode["u8"] = True
+        run_e2e(n_e2e_workers)
+        barrier()
+        t0 = time.perf_counter()
+        h2d_u8, d2h_u8, _ = run_e2e(args.e2e_steps)
+        torch.cuda.synchronize()
+        e2e_u8_s = (time.perf_counter() - t0) / args.e2e_steps
+        e2e_mode["u8"] = False
+        barrier()
 
         # C3 raw coder on EVERY rank (each codes its own 2^28 symbols), max over ranks
         c3 = c3_raw_coder(net, dev, seed=1234 + rank)
@@ -714,7 +747,7 @@ def ours(args, rank, world):
         extra = other_configs(dev) if (rank == 0 and not args.no_variants) else None
         barrier()
 
-    ms, e2e_ms, e2e_host_cpu = max_over_ranks([ms, e2e_s * 1e3, e2e_host_cpu], dev, world)
+    ms, e2e_ms, e2e_host_cpu, e2e_u8_ms = max_over_ranks([ms, e2e_s * 1e3, e2e_host_cpu, e2e_u8_s * 1e3], dev, world)
 
     if rank != 0:
         if world > 1:
@@ -759,6 +792,12 @@ def ours(args, rank, world):
         "e2e": {"value": shard_throughput(mp_step, e2e_ms, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                 "requests_in_flight": n_e2e_workers, "host_cpu_ms_per_request": e2e_host_cpu * 1e3},
+        "e2e_u8": {"value": shard_throughput(mp_step, e2e_u8_ms, world), "unit": UNIT, "h2d_bytes_per_step": h2d_u8,
+                   "d2h_bytes_per_step": d2h_u8, "ms_per_step": e2e_u8_ms, "steps": args.e2e_steps,
+                   "note": "same public-API loop as e2e with uint8 host buffers: compress(uint8 images) converts "
+                           "x / 255 on the device, decompress(out=uint8) returns round(x_hat * 255); the fp32 host "
+                           "tensors of the reference API move 4x the PCIe bytes and at 8 GPUs are bounded by the "
+                           "box's shared host<->device bandwidth (profiles/r02_pcie_probe_8gpu.txt)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv / deconv / fused GDN)", "bound": "tensor",
                      "achieved": conv_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (conv_tf / tpeak) if conv_tf else None,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "cai_eb_quantize_index": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_void_p]),
     "cai_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "cai_pixels_u8_to_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cai_pixels_f32_to_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cai_pmf_to_quantized_cdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                          c_void_p]),
     "cai_gc_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_int64, c_void_p,
@@ -76,6 +78,9 @@ SIGNATURES = {
                               c_void_p, c_void_p]),
     "cai_conv_gemm": (c_int, [POINTER(ConvDesc), c_void_p]),
     "cai_conv_tma_eligible": (c_int, [POINTER(ConvDesc)]),
+    "cai_conv_wgrad_workspace": (c_int64, [c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "cai_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                               c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "cai_split_planes": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "cai_im2col_split": (c_int, [c_void_p] + [c_int32] * 11 + [c_void_p, c_void_p, c_void_p]),
     "cai_col2im": (c_int, [c_void_p, c_void_p] + [c_int32] * 11 + [c_float, c_float, c_void_p, c_void_p]),
@@ -122,7 +127,7 @@ KERNELS_PER_CALL = {"cai_table_create": 3, "cai_rans_encode_batch": 1, "cai_rans
                     "cai_dequantize": 1, "cai_pmf_to_quantized_cdf": 1, "cai_gc_forward": 1, "cai_gc_backward": 1,
                     "cai_eb_forward": 1, "cai_eb_backward": 1, "cai_eb_logits": 1, "cai_conv_gemm": 1,
                     "cai_split_planes": 1, "cai_im2col_split": 1, "cai_col2im": 1, "cai_gdn_bwd_prepare": 1,
-                    "cai_gdn_bwd_finish": 1, "cai_gdn_bwd_params": 1}
+                    "cai_gdn_bwd_finish": 1, "cai_gdn_bwd_params": 1, "cai_conv_wgrad": 4}
 LAUNCHES = 0
 
 

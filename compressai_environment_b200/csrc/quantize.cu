@@ -267,6 +267,47 @@ static int elementwise_grid(const DeviceProps &dp, int64_t work_items, int threa
   return static_cast<int>(g);
 }
 
+
+// 8-bit pixels <-> unit-range floats (the ToTensor() convention of the reference's image pipeline,
+// examples/codec.py:112-128 / utils/eval_model/__main__.py:70-74: x = u8 / 255).  Shipping uint8 over PCIe
+// and converting on the device moves a quarter of the bytes of the fp32 tensor the reference's API takes.
+__global__ void u8_to_unit_kernel(const uint8_t *__restrict__ in, int64_t n, float *__restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n16 = n >> 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4 *o = reinterpret_cast<float4 *>(out) + 4 * i;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      o[q] = make_float4(static_cast<float>(w[q] & 0xFFu) / 255.f, static_cast<float>((w[q] >> 8) & 0xFFu) / 255.f,
+                         static_cast<float>((w[q] >> 16) & 0xFFu) / 255.f, static_cast<float>(w[q] >> 24) / 255.f);
+  }
+  for (int64_t i = (n16 << 4) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = static_cast<float>(in[i]) / 255.f;
+}
+
+__device__ __forceinline__ uint32_t unit_to_u8(float v) {
+  v = fminf(fmaxf(v, 0.f), 1.f);                      // NaN -> 0 (fmaxf returns the non-NaN operand)
+  return static_cast<uint32_t>(__float2int_rn(v * 255.f));  // round half to even, like torch.round
+}
+
+__global__ void unit_to_u8_kernel(const float *__restrict__ in, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n16 = n >> 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 f = __ldg(reinterpret_cast<const float4 *>(in) + 4 * i + q);
+      w[q] = unit_to_u8(f.x) | (unit_to_u8(f.y) << 8) | (unit_to_u8(f.z) << 16) | (unit_to_u8(f.w) << 24);
+    }
+    reinterpret_cast<uint4 *>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int64_t i = (n16 << 4) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = static_cast<uint8_t>(unit_to_u8(in[i]));
+}
+
 }  // namespace cai
 
 using namespace cai;
@@ -352,6 +393,34 @@ int cai_dequantize(const int32_t *sym, const float *means, const float *medians,
     dim3 grid(static_cast<unsigned>((HW + 31) / 32), static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(N));
     deq_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(sym, means, medians, C, HW, out);
   }
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_pixels_u8_to_f32(const uint8_t *in, int64_t n, float *out, cai_stream_t stream_) {
+  CAI_CHECK_ARG(n >= 0, "cai_pixels_u8_to_f32: n < 0");
+  if (n == 0) return CAI_OK;
+  CAI_CHECK_ARG(in && out, "cai_pixels_u8_to_f32: NULL pointer");
+  CAI_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "cai_pixels_u8_to_f32: buffers must be 16-byte aligned");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  u8_to_unit_kernel<<<elementwise_grid(dp, (n + 15) / 16, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(in, n, out);
+  CAI_LAUNCH_CHECK();
+  return CAI_OK;
+}
+
+int cai_pixels_f32_to_u8(const float *in, int64_t n, uint8_t *out, cai_stream_t stream_) {
+  CAI_CHECK_ARG(n >= 0, "cai_pixels_f32_to_u8: n < 0");
+  if (n == 0) return CAI_OK;
+  CAI_CHECK_ARG(in && out, "cai_pixels_f32_to_u8: NULL pointer");
+  CAI_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "cai_pixels_f32_to_u8: buffers must be 16-byte aligned");
+  DeviceProps dp;
+  int rc = get_device_props(&dp);
+  if (rc != CAI_OK) return rc;
+  unit_to_u8_kernel<<<elementwise_grid(dp, (n + 15) / 16, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(in, n, out);
   CAI_LAUNCH_CHECK();
   return CAI_OK;
 }

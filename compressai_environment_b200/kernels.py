@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, check, current_stream, lib, ptr, require_cuda
+from ._lib import CAI_LAYOUT_NCHW, CAI_LAYOUT_NHWC, CaiError, check, current_stream, lib, ptr, require_cuda
 
 
 def _ncs(t: torch.Tensor) -> Tuple[int, int, int]:
@@ -119,4 +119,30 @@ def dequantize(sym: torch.Tensor, means: Optional[torch.Tensor], medians: Option
     with torch.cuda.device(dev):
         check(lib().cai_dequantize(ptr(sym), ptr(tm), ptr(med), layout, N, C, HW, ptr(out), current_stream()),
               "cai_dequantize")
+    return out
+
+
+def pixels_to_float(x_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 image tensor (any shape) -> float32 in [0, 1]: x / 255, the reference callers' ToTensor() convention
+    (examples/codec.py:112-128), computed on the device."""
+    require_cuda(x_u8)
+    if x_u8.dtype != torch.uint8:
+        raise CaiError("pixels_to_float expects a uint8 tensor")
+    x_u8 = x_u8.contiguous()
+    out = torch.empty(x_u8.shape, dtype=torch.float32, device=x_u8.device)
+    with torch.cuda.device(x_u8.device):
+        check(lib().cai_pixels_u8_to_f32(ptr(x_u8), x_u8.numel(), ptr(out), current_stream()), "cai_pixels_u8_to_f32")
+    return out
+
+
+def pixels_to_u8(x: torch.Tensor) -> torch.Tensor:
+    """float32 reconstruction -> uint8: round(clamp(x, 0, 1) * 255) (half to even), computed on the device."""
+    require_cuda(x)
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().cai_pixels_f32_to_u8(ptr(x), x.numel(), ptr(out), current_stream()), "cai_pixels_f32_to_u8")
     return out

@@ -109,6 +109,8 @@ class FactorizedPrior(CompressionModel):
 
     @torch.no_grad()
     def compress(self, x):
+        if x.dtype == torch.uint8:
+            x = kernels.pixels_to_float(x)
         y = self.g_a(_nhwc(x))
         y_strings = self.entropy_bottleneck.compress(y)
         return {"strings": [y_strings], "shape": y.size()[-2:]}
@@ -260,7 +262,8 @@ class ScaleHyperprior(CompressionModel):
 
     @torch.no_grad()
     def compress_to_device(self, x):
-        """compress() with the strings left in HBM: per micro-batch ``coder.EncodedBatch`` lists."""
+        """compress() with the strings left in HBM: per micro-batch ``coder.EncodedBatch`` lists.  ``x`` float32 in
+        [0, 1] as in the reference, or uint8 pixels (host or device), converted on the device as x / 255."""
         self._check_tables()
         host_in = not x.is_cuda
         dev = self.gaussian_conditional._quantized_cdf.device if host_in else x.device
@@ -289,6 +292,8 @@ class ScaleHyperprior(CompressionModel):
             else:
                 xc = x[i:i + self.micro_batch]
             with torch.cuda.stream(ana):
+                if xc.dtype == torch.uint8:  # 8-bit pixels: x = u8 / 255 on the device (ToTensor convention)
+                    xc = kernels.pixels_to_float(xc)
                 y_sym, y_idx, z_sym, z_idx, shape = self._analysis_chunk(xc)
                 self._handoff(ck, y_sym, y_idx, z_sym, z_idx)
             with torch.cuda.stream(ck):
@@ -375,6 +380,8 @@ class ScaleHyperprior(CompressionModel):
                 else:
                     # host output buffer (serving path): this micro-batch goes home while the next one is synthesised
                     d2h = S["d2h"]
+                    if out.dtype == torch.uint8:  # 8-bit result: round(x_hat * 255) on the device, 1/4 of the bytes
+                        xc = kernels.pixels_to_u8(xc)
                     d2h.wait_event(syn.record_event())
                     with torch.cuda.stream(d2h):
                         out[row:row + xc.size(0)].copy_(xc, non_blocking=True)
@@ -390,7 +397,8 @@ class ScaleHyperprior(CompressionModel):
     @torch.no_grad()
     def decompress(self, strings, shape, out=None):
         """``out``: optional preallocated CPU tensor [B, 3, H, W] (pinned for asynchronous copies) that receives the
-        reconstruction micro-batch by micro-batch; the returned ``x_hat`` is then ``out`` itself."""
+        reconstruction micro-batch by micro-batch; the returned ``x_hat`` is then ``out`` itself.  A uint8 ``out``
+        receives round(x_hat * 255), converted on the device (a quarter of the PCIe bytes)."""
         assert isinstance(strings, list) and len(strings) == 2
         self._check_tables()
         if len(strings[0]) != len(strings[1]):
@@ -407,8 +415,9 @@ class ScaleHyperprior(CompressionModel):
             ys, zs = (v if isinstance(v, coder.PackedStrings) else list(v) for v in (ys, zs))
             chunks.append((coder_streams[k], (ys, None), (zs, None), len(ys)))
         statuses = []
-        if out is not None and (out.is_cuda or out.dim() != 4 or out.size(0) != n or out.dtype != torch.float32):
-            raise ValueError("out must be a float32 CPU tensor [len(strings[0]), 3, H, W]")
+        if out is not None and (out.is_cuda or out.dim() != 4 or out.size(0) != n
+                                or out.dtype not in (torch.float32, torch.uint8)):
+            raise ValueError("out must be a float32 or uint8 CPU tensor [len(strings[0]), 3, H, W]")
         res = self._decompress_chunks(chunks, shape, dev, statuses, out)
         coder.wait_stream(torch.cuda.current_stream(dev))  # one (non-spinning) sync per call: surface decoder errors
         coder.check_status(statuses)

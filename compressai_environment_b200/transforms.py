@@ -15,8 +15,10 @@ weights are split and tiled once per parameter version (``pack_weights``) into t
   Cin=3 first layer  -> im2col to K=80 + 1x1 GEMM;  Cout=3 last layer -> 1x1 GEMM to N=80 + col2im gather
 ReLU / LeakyReLU / abs / clamp are folded into the producing launch's epilogue.
 
-Training (autograd) uses the same kernels for the forward of GDN/likelihoods; the convolution backward is not
-on the hot path named by BASELINE.json and is delegated to torch autograd (library call).
+Training (autograd): ``_ConvFunction`` runs the forward on the same implicit-GEMM kernel, the data gradient as the
+OTHER layer kind's forward with the same weights (dgrad of a conv is a transposed conv and vice versa), and the weight
+gradient on the tcgen05 pixel-reduction GEMM of csrc/wgrad.cu (``cai_conv_wgrad``); GDN and the likelihoods have their
+own forward / backward kernels.  No cuDNN call is left on the training step's transforms.
 """
 from __future__ import annotations
 
@@ -62,8 +64,8 @@ class Conv2d(_cache.CacheOwner, nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, x: Tensor) -> Tensor:
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
-            return F.conv2d(x, self.weight, self.bias, stride=self.stride, padding=self.padding)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad or self.bias.requires_grad):
+            return _ConvFunction.apply(x, self.weight, self.bias, self)  # forward, dgrad and wgrad on our kernels
         return run_stack([self], x)
 
     def extra_repr(self):
@@ -88,9 +90,8 @@ class ConvTranspose2d(_cache.CacheOwner, nn.Module):
         nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, x: Tensor) -> Tensor:
-        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
-            return F.conv_transpose2d(x, self.weight, self.bias, stride=self.stride, padding=self.padding,
-                                      output_padding=self.output_padding)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad or self.bias.requires_grad):
+            return _ConvFunction.apply(x, self.weight, self.bias, self)  # forward, dgrad and wgrad on our kernels
         return run_stack([self], x)
 
     def extra_repr(self):
@@ -235,6 +236,7 @@ class _Layer:
     def __init__(self, kind, packed, bias, taps_per_phase, bn, cin, cout, geom, packed_c=None):
         self.kind, self.packed, self.bias, self.phases, self.bn = kind, packed, bias, taps_per_phase, bn
         self.cin, self.cout, self.geom = cin, cout, geom
+        self.true_cout = cout  # un-padded output channels (set by the builders)
         # the same weights with k-steps in the persistent TMA kernel's order (None: identical to `packed`)
         self.packed_c = packed_c if packed_c is not None else packed
 
@@ -266,6 +268,7 @@ def _build_conv(m: "Conv2d") -> _Layer:
         wpad = _pad_taps(wt, cp, kp)
         lay = _Layer("conv", pack_weights(wpad, bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
                      (k, s, p), packed_c=pack_weights(wpad, bn, taps.glen, order="chunk"))
+    lay.true_cout = cout
     return lay
 
 
@@ -305,6 +308,7 @@ def _build_deconv(m: "ConvTranspose2d") -> _Layer:
                 blobs.append(pack_weights(wpad, bn, taps.glen) if ws else None)
                 blobs_c.append(pack_weights(wpad, bn, taps.glen, order="chunk") if ws else None)
         lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op), packed_c=blobs_c)
+    lay.true_cout = cout
     return lay
 
 
@@ -380,8 +384,8 @@ def _outputs(N, Ho, Wo, C, device, want):
 
 def _run_conv(m, x, act, want, clamp=None, gdn=None):
     """x: Planes (or fp32 tensor for the im2col first layer). Returns (f32 NHWC tensor | None, planes, sq, abs)."""
-    lay = _prep_conv(m)
-    dev = m.weight.device
+    lay = m if isinstance(m, _Layer) else _prep_conv(m)
+    dev = lay.bias.device
     if lay.kind == "conv_im2col":
         k, s, p, kpad = lay.geom
         if isinstance(x, Planes):
@@ -414,8 +418,8 @@ def _run_conv(m, x, act, want, clamp=None, gdn=None):
 
 
 def _run_deconv(m, x, act, want, clamp=None, final_layout_nchw=False, gdn=None, dst=None):
-    lay = _prep_deconv(m)
-    dev = m.weight.device
+    lay = m if isinstance(m, _Layer) else _prep_deconv(m)
+    dev = lay.bias.device
     if not isinstance(x, Planes):
         x = to_planes(x, lay.cin)
     if lay.kind == "deconv_col2im":
@@ -590,6 +594,100 @@ def _planes_of(xn: Tensor) -> Planes:
         check(lib().cai_split_planes(ptr(xn), CAI_LAYOUT_NHWC, N, C, H * W, C, ptr(out.hi), ptr(out.lo), current_stream()),
               "cai_split_planes")
     return out
+
+
+# ---- training mode: conv / transposed conv with all three GEMMs on this package's kernels ---------------------
+def _run_conv_layer(lay: "_Layer", x: Tensor) -> Tensor:
+    """One prepared conv layer on an fp32 tensor -> logical-NCHW fp32 result (true channel count)."""
+    o = _run_conv(lay, x, None, ("f32",))
+    return o[0].permute(0, 3, 1, 2)[:, :lay.true_cout]
+
+
+def _run_deconv_layer(lay: "_Layer", x: Tensor) -> Tensor:
+    o = _run_deconv(lay, x, None, ("f32",), final_layout_nchw=True)
+    out = o[0]
+    if lay.kind != "deconv_col2im":
+        out = out.permute(0, 3, 1, 2)
+    return out[:, :lay.true_cout]
+
+
+class _LayerShim:
+    """The attributes ``_build_conv`` / ``_build_deconv`` read from a module: lets the data gradient reuse the forward
+    kernels with the SAME weight tensor (a conv's weight [Cout, Cin, k, k] is a transposed conv's [in, out, k, k] with
+    in = Cout, and vice versa) and a zero bias."""
+
+    def __init__(self, weight, in_channels, out_channels, k, s, p, op=0):
+        self.weight, self.in_channels, self.out_channels = weight, in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.output_padding = k, s, p, op
+        self.bias = torch.zeros(out_channels, dtype=torch.float32, device=weight.device)
+
+
+def conv_wgrad(small: Tensor, big: Tensor, k: int, s: int, p: int) -> Tensor:
+    """grad[cs, cb, ky, kx] = sum_{n,i,j} small[n,cs,i,j] * big[n,cb, s*i+ky-p, s*j+kx-p]  (``cai_conv_wgrad``)."""
+    require_cuda(small, "gradients")
+    small = small.detach().float().contiguous()
+    big = big.detach().float().contiguous()
+    N, Cs, Hs, Ws = small.shape
+    Nb, Cb, Hb, Wb = big.shape
+    if N != Nb:
+        raise _lib.CaiError("conv_wgrad: batch sizes differ")
+    dev = small.device
+    with torch.cuda.device(dev):
+        need = lib().cai_conv_wgrad_workspace(N, Cs, Hs, Ws, Cb, Hb, Wb, k, s)
+        if need < 0:
+            check(-1, "cai_conv_wgrad_workspace")
+        ws = torch.empty(int(need) + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        grad = torch.empty((Cs, Cb, k, k), dtype=torch.float32, device=dev)
+        check(lib().cai_conv_wgrad(ptr(small), ptr(big), N, Cs, Hs, Ws, Cb, Hb, Wb, k, s, p, ptr(grad),
+                                   _lib.c_void_p(ws.data_ptr() + off), int(need), current_stream()), "cai_conv_wgrad")
+    return grad
+
+
+class _ConvFunction(torch.autograd.Function):
+    """``Conv2d`` / ``ConvTranspose2d`` in training mode (autograd of compressai/models/utils.py:128-146 layers as
+    driven by examples/train.py:132-165).  forward: the inference kernel.  backward: dX = the other layer kind's
+    forward on dY with the same weights; dW = ``cai_conv_wgrad``; db = per-channel sum of dY."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        require_cuda(x, "inputs")
+        with torch.no_grad():
+            out = run_stack([mod], x)
+        ctx.save_for_backward(x, weight)
+        ctx.mod = mod
+        # run_stack returns a permuted view of its NHWC buffer; an in-place op on a view created inside a custom
+        # Function (nn.ReLU(inplace=True) follows the hyper-transform layers) is refused by autograd, so hand out a
+        # plain tensor over the same storage instead
+        res = torch.empty(0, dtype=out.dtype, device=out.device)
+        res.set_(out.untyped_storage(), out.storage_offset(), out.size(), out.stride())
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        m = ctx.mod
+        k, s, p = m.kernel_size, m.stride, m.padding
+        transposed = isinstance(m, ConvTranspose2d)
+        g = g.detach()
+        gx = gw = gb = None
+        with torch.no_grad():
+            if ctx.needs_input_grad[0]:
+                if transposed:   # dX = conv2d(dY, W): W [Cin, Cout, k, k] read as a conv weight [out = Cin, in = Cout]
+                    shim = _LayerShim(weight.detach(), m.out_channels, m.in_channels, k, s, p)
+                    gx = _run_conv_layer(_build_conv(shim), g)
+                else:            # dX = conv_transpose2d(dY, W): W [Cout, Cin, k, k] read as [in = Cout, out = Cin]
+                    op = x.size(2) - ((g.size(2) - 1) * s - 2 * p + k)
+                    opw = x.size(3) - ((g.size(3) - 1) * s - 2 * p + k)
+                    if op != opw or not 0 <= op < max(s, 1):
+                        raise _lib.CaiError("conv backward: input size is not reachable by a transposed convolution")
+                    shim = _LayerShim(weight.detach(), m.out_channels, m.in_channels, k, s, p, op)
+                    gx = _run_deconv_layer(_build_deconv(shim), g)
+            if ctx.needs_input_grad[1]:
+                gw = conv_wgrad(x, g, k, s, p) if transposed else conv_wgrad(g, x, k, s, p)
+            if ctx.needs_input_grad[2]:
+                gb = g.float().sum(dim=(0, 2, 3))
+        return gx, gw, gb, None
 
 
 class _GDNFunction(torch.autograd.Function):

@@ -156,6 +156,13 @@ int cai_eb_quantize_index(const float *x, const float *medians, int32_t layout, 
 int cai_dequantize(const int32_t *sym, const float *means, const float *medians, int32_t layout,
                    int64_t N, int64_t C, int64_t HW, float *out, cai_stream_t stream);
 
+/* 8-bit pixels <-> unit-range fp32 on the device: out = in / 255 (the ToTensor() convention the reference's callers
+ * apply on the host before model.compress, examples/codec.py:112-128) and out = round_half_even(clamp(in, 0, 1) * 255)
+ * (NaN -> 0).  They let the serving path move uint8 images over PCIe (a quarter of the fp32 bytes).  n elements,
+ * any layout; both buffers 16-byte aligned. */
+int cai_pixels_u8_to_f32(const uint8_t *in, int64_t n, float *out, cai_stream_t stream);
+int cai_pixels_f32_to_u8(const float *in, int64_t n, uint8_t *out, cai_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Table build.  pmf_to_quantized_cdf (compressai/cpp_exts/ops/ops.cpp:40-109) for K rows at once with
  * the caller's row convention of EntropyModel._pmf_to_cdf (entropy_models.py:204-212):
@@ -271,6 +278,22 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream);
  * channels in one tile of at most 128, input stride 1 or 2, grouped taps, 16-byte aligned planes), else 0.  The caller
  * then packs the weights in the order of mode 1 and sets d->mode = 1. */
 int cai_conv_tma_eligible(const cai_conv_desc *d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training mode: weight gradient of a conv / transposed conv (csrc/wgrad.cu), replacing the cuDNN call behind
+ * autograd of nn.Conv2d / nn.ConvTranspose2d (compressai/models/utils.py:128-146, examples/train.py:132-165):
+ *   grad[cs][cb][ky][kx] = sum_{n,i,j} small[n,cs,i,j] * big[n,cb, stride*i + ky - pad, stride*j + kx - pad]
+ * small fp32 NCHW [N, Cs, Hs, Ws] = dY of a conv / X of a transposed conv; big fp32 NCHW [N, Cb, Hb, Wb] = X of a conv /
+ * dY of a transposed conv; grad fp32 [Cs, Cb, ksize, ksize] = the layer's weight gradient in torch's layout for both
+ * kinds.  stride 1 or 2, ksize^2 <= 32.  workspace: device scratch of cai_conv_wgrad_workspace() bytes (256-byte
+ * aligned; split bf16 operand planes + split-K partial sums).  The data gradient of either layer kind is the other
+ * kind's forward (cai_conv_gemm with the same weights).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t cai_conv_wgrad_workspace(int64_t N, int32_t Cs, int32_t Hs, int32_t Ws, int32_t Cb, int32_t Hb, int32_t Wb,
+                                 int32_t ksize, int32_t stride);
+int cai_conv_wgrad(const float *small, const float *big, int64_t N, int32_t Cs, int32_t Hs, int32_t Ws, int32_t Cb,
+                   int32_t Hb, int32_t Wb, int32_t ksize, int32_t stride, int32_t pad, float *grad, void *workspace,
+                   int64_t workspace_bytes, cai_stream_t stream);
 
 /* fp32 latent / image (layout NCHW or NHWC) -> split planes [N, HW, Cpad] (channels zero padded to Cpad) */
 int cai_split_planes(const float *x, int32_t layout, int64_t N, int64_t C, int64_t HW, int64_t Cpad, void *hi, void *lo,

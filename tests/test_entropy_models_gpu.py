@@ -368,3 +368,24 @@ def _apply_mode2(gc, y, s, m):
     from compressai_environment_b200.entropy_models.entropy_models import _GaussianLikelihood
 
     return _GaussianLikelihood.apply(y, s, m, None, 2, gc._bound_scale(), gc._lik_bound())
+
+
+def test_pixel_conversions_exact():
+    """cai_pixels_u8_to_f32 / cai_pixels_f32_to_u8 against the torch definitions (ToTensor's x / 255; round half to
+    even of clamp(x, 0, 1) * 255), including ragged tails, NaN and out-of-range values."""
+    from compressai_environment_b200 import kernels
+
+    g = torch.Generator().manual_seed(5)
+    for n in (0, 1, 15, 16, 17, 4099, 3 * 37 * 53):
+        u_cpu = torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
+        u = u_cpu.to(DEV)
+        f = kernels.pixels_to_float(u)
+        # the reference's callers convert on the HOST (ToTensor): a true IEEE division.  (torch's CUDA division by a
+        # scalar multiplies by the reciprocal instead and differs in the last bit for 126 of the 256 values.)
+        assert torch.equal(f.cpu(), u_cpu.float() / 255.0)
+        assert torch.equal(kernels.pixels_to_u8(f), u)
+        x = (torch.rand(n, generator=g) * 1.4 - 0.2).to(DEV)
+        if n > 3:
+            x[1], x[2], x[3] = float("nan"), 0.5 / 255.0, 1.5 / 255.0   # NaN -> 0; ties go to the even value
+        want = (torch.nan_to_num(x.cpu(), nan=0.0).clamp(0, 1) * 255.0).round().to(torch.uint8)
+        assert torch.equal(kernels.pixels_to_u8(x).cpu(), want)
