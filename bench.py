@@ -997,6 +997,8 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="codec", choices=["codec", "train"],
+                    help="codec: compress+decompress (C2, the headline); train: C5 training step under DDP (bench_train.py)")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=30)
@@ -1017,6 +1019,12 @@ def main():
     globals().update(GAIN_Y=args.gain_y, GAIN_S=args.gain_s)
     if args.cpu_coder_leg:
         print(json.dumps(cpu_coder_leg()), flush=True)
+        return
+    if args.mode == "train":
+        import bench_train
+
+        sys.modules.setdefault("bench", sys.modules[__name__])  # bench_train reuses this module's helpers
+        bench_train.main(args)
         return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -201,6 +201,23 @@ def _grouped(taps, rows, step: int):
     return out, [rows[i] for i in order]
 
 
+_SCHED_CACHE = {}
+
+
+def _group_schedule(glen, kc: int, device) -> Tensor:
+    """Index tensor of the "group" k-step order (cached per shape and device: building it from a Python list costs a
+    synchronous host-to-device copy, which a training step would pay for every layer, every step)."""
+    key = (glen, kc, str(device))
+    idx = _SCHED_CACHE.get(key)
+    if idx is None:
+        sched, t0 = [], 0
+        for g in glen:
+            sched += [t * kc + c for c in range(kc) for t in range(t0, t0 + g)]
+            t0 += g
+        idx = _SCHED_CACHE[key] = torch.tensor(sched, device=device)
+    return idx
+
+
 def pack_weights(w_taps: Tensor, bn: int, glen=None, order: str = "group") -> Tensor:
     """w_taps fp32 [T, Cout, Cin] -> uint8 blob [n_tiles][k-step][hi | lo][BN x 32 bf16] in the UMMA canonical
     K-major order: element (r, k) of a tile at ((k // 8) * BN * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2).
@@ -221,12 +238,8 @@ def pack_weights(w_taps: Tensor, bn: int, glen=None, order: str = "group") -> Te
             packed = packed.transpose(1, 2)  # nt, kc, T, ...
     elif glen is not None and any(g > 1 for g in glen):
         assert sum(glen) == T
-        sched, t0 = [], 0
-        for g in glen:
-            sched += [t * kc + c for c in range(kc) for t in range(t0, t0 + g)]
-            t0 += g
         flat = packed.reshape(nt, T * kc, *packed.shape[3:])
-        packed = flat[:, torch.tensor(sched, device=flat.device)]
+        packed = flat[:, _group_schedule(tuple(glen), kc, flat.device)]
     return packed.contiguous().view(torch.uint8).reshape(-1)
 
 
@@ -237,8 +250,10 @@ class _Layer:
         self.kind, self.packed, self.bias, self.phases, self.bn = kind, packed, bias, taps_per_phase, bn
         self.cin, self.cout, self.geom = cin, cout, geom
         self.true_cout = cout  # un-padded output channels (set by the builders)
-        # the same weights with k-steps in the persistent TMA kernel's order (None: identical to `packed`)
-        self.packed_c = packed_c if packed_c is not None else packed
+        # the same weights with k-steps in the persistent TMA kernel's order; None = not built (the layer then stays on
+        # the per-tile kernel).  Single-tap layers share one order; multi-tap layers build it only under
+        # TMA_POLICY == "all" (a training step repacks every layer's weights every step)
+        self.packed_c = packed_c
 
 
 def _prep_conv(m: "Conv2d") -> _Layer:
@@ -256,8 +271,8 @@ def _build_conv(m: "Conv2d") -> _Layer:
         wt = w.permute(0, 2, 3, 1).reshape(1, cout, kflat)  # k index = (ky*k + kx)*cin + ci
         cp = _c16(cout)
         bn = _choose_bn(cp)
-        lay = _Layer("conv_im2col", pack_weights(_pad_taps(wt, cp, kflat), bn), _pad_vec(m.bias, cp), [[(0, 0)]], bn,
-                     kpad, cp, (k, s, p, kpad))
+        blob = pack_weights(_pad_taps(wt, cp, kflat), bn)
+        lay = _Layer("conv_im2col", blob, _pad_vec(m.bias, cp), [[(0, 0)]], bn, kpad, cp, (k, s, p, kpad), packed_c=blob)
     else:
         wt = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
         taps = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
@@ -267,7 +282,7 @@ def _build_conv(m: "Conv2d") -> _Layer:
         bn = _choose_bn(cp)
         wpad = _pad_taps(wt, cp, kp)
         lay = _Layer("conv", pack_weights(wpad, bn, taps.glen), _pad_vec(m.bias, cp), [taps], bn, kp, cp,
-                     (k, s, p), packed_c=pack_weights(wpad, bn, taps.glen, order="chunk"))
+                     (k, s, p), packed_c=pack_weights(wpad, bn, taps.glen, order="chunk") if TMA_POLICY == "all" else None)
     lay.true_cout = cout
     return lay
 
@@ -284,8 +299,9 @@ def _build_deconv(m: "ConvTranspose2d") -> _Layer:
         nflat = k * k * cout
         npad = (nflat + 15) // 16 * 16
         wt = w.permute(2, 3, 1, 0).reshape(1, nflat, cin)  # row index = (ky*k + kx)*cout + co
-        lay = _Layer("deconv_col2im", pack_weights(_pad_taps(wt, npad, _c16(cin)), npad),
-                     m.bias.detach().float().contiguous(), [[(0, 0)]], npad, _c16(cin), cout, (k, s, p, op, npad))
+        blob = pack_weights(_pad_taps(wt, npad, _c16(cin)), npad)
+        lay = _Layer("deconv_col2im", blob, m.bias.detach().float().contiguous(), [[(0, 0)]], npad, _c16(cin), cout,
+                     (k, s, p, op, npad), packed_c=blob)
     else:
         cp, kp = _c16(cout), _c16(cin)
         bn = _choose_bn(cp)
@@ -306,7 +322,7 @@ def _build_deconv(m: "ConvTranspose2d") -> _Layer:
                 phases.append(taps)
                 wpad = _pad_taps(torch.stack(ws, 0), cp, kp) if ws else None
                 blobs.append(pack_weights(wpad, bn, taps.glen) if ws else None)
-                blobs_c.append(pack_weights(wpad, bn, taps.glen, order="chunk") if ws else None)
+                blobs_c.append(pack_weights(wpad, bn, taps.glen, order="chunk") if (ws and TMA_POLICY == "all") else None)
         lay = _Layer("deconv", blobs, _pad_vec(m.bias, cp), phases, bn, kp, cp, (k, s, p, op), packed_c=blobs_c)
     lay.true_cout = cout
     return lay
@@ -738,13 +754,14 @@ class _GDNFunction(torch.autograd.Function):
         _launch(tp, pack_weights(gam.transpose(1, 2).contiguous(), bn), None, [(0, 0)], bn, cp, H, W, H, W, 1, 0, 0, 1, 0,
                 None, u, None, None, None)
         gx = torch.empty_like(xn)
-        g_beta = torch.empty(cp, dtype=torch.float32, device=dev)
-        g_gamma = torch.empty((cp, cp), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib().cai_gdn_bwd_finish(ptr(p), ptr(xn), ptr(u), int(inverse), n_el, ptr(gx), current_stream()),
                   "cai_gdn_bwd_finish")
-            check(lib().cai_gdn_bwd_params(ptr(t), ptr(xn), N * H * W, cp, int(inverse), ptr(g_beta), ptr(g_gamma),
-                                           current_stream()), "cai_gdn_bwd_params")
+        # dgamma[i, j] = -+1/2 sum_pixels t_i x_j^2 is the weight gradient of a 1x1 convolution: the same tcgen05
+        # pixel-reduction GEMM as the conv layers (cai_conv_wgrad); dbeta_i = -+1/2 sum_pixels t_i
+        half = 0.5 if inverse else -0.5
+        g_gamma = conv_wgrad(t.permute(0, 3, 1, 2), (xn * xn).permute(0, 3, 1, 2), 1, 1, 0).reshape(cp, cp) * half
+        g_beta = t.sum(dim=(0, 1, 2)) * half
         return gx[..., :C].permute(0, 3, 1, 2), g_beta[:C], g_gamma[:C, :C], None
 
 
