@@ -722,12 +722,14 @@ def ours(args, rank, world):
         barrier()
         # the same loop with 8-bit host buffers (uint8 images in, uint8 reconstruction out)
         e2e_mode["u8"] = True
-        run_e2e(n_e2e_workers)
+        run_e2e(2 * n_e2e_workers)
         barrier()
+        seg0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         t0 = time.perf_counter()
         h2d_u8, d2h_u8, _ = run_e2e(args.e2e_steps)
         torch.cuda.synchronize()
         e2e_u8_s = (time.perf_counter() - t0) / args.e2e_steps
+        e2e_u8_cudamallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - seg0
         e2e_mode["u8"] = False
         barrier()
 
@@ -794,6 +796,7 @@ def ours(args, rank, world):
                 "requests_in_flight": n_e2e_workers, "host_cpu_ms_per_request": e2e_host_cpu * 1e3},
         "e2e_u8": {"value": shard_throughput(mp_step, e2e_u8_ms, world), "unit": UNIT, "h2d_bytes_per_step": h2d_u8,
                    "d2h_bytes_per_step": d2h_u8, "ms_per_step": e2e_u8_ms, "steps": args.e2e_steps,
+                   "cudamallocs_in_timed_region": e2e_u8_cudamallocs,
                    "note": "same public-API loop as e2e with uint8 host buffers: compress(uint8 images) converts "
                            "x / 255 on the device, decompress(out=uint8) returns round(x_hat * 255); the fp32 host "
                            "tensors of the reference API move 4x the PCIe bytes and at 8 GPUs are bounded by the "

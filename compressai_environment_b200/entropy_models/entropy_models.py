@@ -22,6 +22,8 @@ from typing import Any, Callable, List, Optional, Tuple, Union
 
 import numpy as np
 import scipy.stats
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -274,6 +276,26 @@ class EntropyModel(_cache.CacheOwner, nn.Module):
         return out.type(dtype)
 
 
+
+# Where the additive uniform noise of training-mode quantisation is drawn.  "device" (default): on the GPU, from the
+# CUDA generator.  "cpu": from torch's CPU generator in the element order the reference draws it -- (C, B, ...) for
+# the EntropyBottleneck (it permutes before quantising, entropy_models.py:478-492) and (B, C, ...) for the
+# GaussianConditional (:161-165) -- so that a seeded run consumes the same random stream as the reference on CPU and
+# reproduces its training log (tests/test_insitu_train_gpu.py).  Parity aid only: it adds a host-to-device copy.
+NOISE_RNG = os.environ.get("CAI_NOISE_RNG", "device")
+
+
+def _training_noise(x: Tensor, channel_major: bool) -> Tensor:
+    if NOISE_RNG != "cpu":
+        return torch.empty_like(x).uniform_(-0.5, 0.5)
+    if channel_major and x.dim() >= 2:
+        n = torch.empty((x.size(1), x.size(0), *x.shape[2:]), dtype=torch.float32).uniform_(-0.5, 0.5).transpose(0, 1)
+    else:
+        n = torch.empty(tuple(x.shape), dtype=torch.float32).uniform_(-0.5, 0.5)
+    out = torch.empty_like(x)
+    out.copy_(n)
+    return out
+
 # ---- fused likelihood autograd functions -----------------------------------------------------------------
 class _GaussianLikelihood(torch.autograd.Function):
     """quantize + GaussianConditional._likelihood + LowerBound in one kernel each way (cai_gc_forward/backward)."""
@@ -497,7 +519,7 @@ class EntropyBottleneck(EntropyModel):
         if training is None:
             training = self.training
         require_cuda(x, "inputs")
-        noise = torch.empty_like(x).uniform_(-0.5, 0.5) if training else None
+        noise = _training_noise(x, channel_major=True) if training else None
         outputs, likelihood = _BottleneckLikelihood.apply(x, self._tparams(False), self._get_medians(), noise,
                                                           0 if training else 1, self._lik_bound(), self.filters)
         return outputs, likelihood
@@ -641,7 +663,7 @@ class GaussianConditional(EntropyModel):
                 training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:
         if training is None:
             training = self.training
-        noise = torch.empty_like(inputs).uniform_(-0.5, 0.5) if training else None
+        noise = _training_noise(inputs, channel_major=False) if training else None
         outputs, likelihood = _GaussianLikelihood.apply(inputs, scales, means, noise, 0 if training else 1,
                                                         self._bound_scale(), self._lik_bound())
         return outputs, likelihood

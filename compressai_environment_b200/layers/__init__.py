@@ -1,3 +1,4 @@
 from .gdn import GDN
+from .layers import QReLU
 
-__all__ = ["GDN"]
+__all__ = ["GDN", "QReLU"]

@@ -42,3 +42,6 @@ models = {
     "bmshj2018-hyperprior": bmshj2018_hyperprior,
     "mbt2018-mean": mbt2018_mean,
 }
+
+# the name the reference's zoo exports (compressai/zoo/__init__.py) and its examples import
+image_models = models

@@ -34,4 +34,10 @@ mkdir -p "$OUT/tests"
 for t in test_entropy_models.py test_ops.py test_coder.py; do
   cp "$REF/tests/$t" "$OUT/tests/$t"
 done
+# The reference's training example, its fake dataset and the expected log of its own training test
+# (tests/test_train.py:40-88), for tests/test_insitu_train_gpu.py: the UNMODIFIED script drives this repo's models.
+mkdir -p "$OUT/examples" "$OUT/tests/assets/fakedata" "$OUT/tests/expected"
+cp "$REF/examples/train.py" "$OUT/examples/train.py"
+cp -r "$REF/tests/assets/fakedata/imagefolder" "$OUT/tests/assets/fakedata/imagefolder"
+cp "$REF/tests/expected/train_log_3.14.txt" "$OUT/tests/expected/train_log_3.14.txt"
 echo "build_ref: reference installed in $OUT"
