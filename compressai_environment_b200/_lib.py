@@ -42,6 +42,14 @@ class ConvDesc(Structure):
                    ("gdn_w", c_void_p), ("gdn_beta", c_void_p), ("gdn_mode", c_int32), ("mode", c_int32)])
 
 
+class ArDesc(Structure):
+    """Mirror of ``cai_ar_desc`` (include/cai_b200.h)."""
+    _fields_ = ([(n, c_void_p) for n in ("w_ctx", "b_ctx", "w1", "b1", "w2", "b2", "w3", "b3", "params", "scale_table")]
+                + [("scale_bound", c_float), ("slope", c_float)]
+                + [(n, c_int32) for n in ("T", "B", "H", "W", "M", "P", "n_ctx", "n1", "n2", "n3", "ksize", "cluster",
+                                          "group")])
+
+
 # name -> (restype, argtypes).  Must list every symbol declared in include/cai_b200.h
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 SIGNATURES = {
@@ -88,6 +96,8 @@ SIGNATURES = {
                                     c_void_p]),
     "cai_gdn_bwd_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "cai_gdn_bwd_params": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cai_ar_encode": (c_int, [POINTER(ArDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cai_ar_decode": (c_int, [POINTER(ArDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

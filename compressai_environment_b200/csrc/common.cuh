@@ -66,6 +66,7 @@ struct Knobs {
   int coder_lanes = 0;      // CAI_CODER_LANES   (N > 0: lane-per-string kernels from N strings per launch up; 0 = never, the default)
   int conv_persist = -1;    // CAI_CONV_PERSIST  (-1 = automatic)
   int coder_lut_adapt = -1; // CAI_LUT_ADAPT     (-1 = automatic)
+  int tma_epi_warps = 0;    // CAI_TMA_EPI_WARPS (8 or 16 epilogue warps in the persistent transform kernel; 0 = 16)
 };
 const Knobs &knobs();
 

@@ -31,9 +31,11 @@
 
 namespace cai {
 
-constexpr int kTmaEpiWarps = 8;
-constexpr int kTmaEpiThreads = kTmaEpiWarps * 32;
-constexpr int kTmaThreads = kTmaEpiThreads + 64;  // + warp 8: TMA producer, warp 9: MMA issuer (owns TMEM)
+// Epilogue warps per CTA: template parameter EW = 8 or 16 (EW / 4 "groups" per TMEM lane quarter; group h takes every
+// (EW/4)-th 32-column slab and owns x^2 slab buffer h).  The epilogue of the short-K layers is bound by instruction issue
+// with few warps per scheduler (ncu r02: 0.39 IPC per sub-partition with 8 warps): 16 warps double the issue supply.
+// Two more warps follow: warp EW = TMA producer, warp EW + 1 = MMA issuer (owns TMEM).
+constexpr int kTmaMaxGroups = 4;
 constexpr int kMaxRing = 8;
 
 struct TmaConvParams {
@@ -77,13 +79,17 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, i
 }
 
 // KIND: 1 fused GDN / IGDN -> split planes; 2 linear / ReLU / LeakyReLU -> split planes; 3 -> fp32 (+ |.| planes, clamp)
-template <int KIND>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+template <int KIND, int EW>
+__global__ void __launch_bounds__(EW * 32 + 64, 1)
 conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t a_full[kMaxRing], a_empty[kMaxRing], b_full[kMaxRing], b_empty[kMaxRing];
-  __shared__ __align__(8) uint64_t acc_full[2], acc_free[2], slab_full[2], slab_free[2], norm_full[2], gamma_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_free[2], slab_full[kTmaMaxGroups], slab_free[kTmaMaxGroups], norm_full[2], gamma_bar;
+  constexpr int kTmaEpiWarps = EW;
+  constexpr int kTmaEpiThreads = EW * 32;
+  constexpr int kGroups = EW / 4;
+  static_assert(kGroups >= 1 && kGroups <= kTmaMaxGroups && (kGroups & (kGroups - 1)) == 0, "EW must be 4, 8 or 16");
   __shared__ uint32_t s_tmem_base;
   __shared__ int64_t s_opix[kBM];
   __shared__ __align__(16) float s_bias[128];
@@ -117,9 +123,11 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_free[s], 1);
+      mbar_init(&norm_full[s], 1);
+    }
+    for (int s = 0; s < kGroups; ++s) {
       mbar_init(&slab_full[s], 128);
       mbar_init(&slab_free[s], 1);
-      mbar_init(&norm_full[s], 1);
     }
     mbar_init(&gamma_bar, 1);
     mbar_fence_init();
@@ -204,10 +212,10 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
       uint32_t a_par = 0, b_par = 0;
       // GDN products still owed to an earlier tile (its x^2 slabs are written by the epilogue warps)
       int g_next = gk, g_set = 0;
-      uint32_t g_use[2] = {0u, 0u};  // completed uses of slab buffer 0 / 1 (phase of slab_full)
+      uint32_t g_use[kGroups] = {};  // completed uses of each slab buffer (phase of slab_full)
       auto gdn_issue = [&](bool block) {
         while (g_next < gk) {
-          const int buf = g_next & 1;
+          const int buf = g_next & (kGroups - 1);
           if (block) mbar_wait_bounded(&slab_full[buf], g_use[buf] & 1);
           else if (!mbar_test(&slab_full[buf], g_use[buf] & 1)) return;
           tc_fence_after();
@@ -319,7 +327,7 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
         // x = acc + bias; x^2 split into bf16 planes -> slab buffer h, one 32-column slab per GDN k-step
         uint32_t raw[32];
 #pragma unroll 1
-        for (int g = h; g < gk; g += 2) {
+        for (int g = h; g < gk; g += kGroups) {
           if (slab_uses > 0) mbar_wait_bounded(&slab_free[h], (slab_uses - 1) & 1);
           unsigned char *sl = sm_e + static_cast<uint32_t>(h) * (2u * slab_plane);
           const int col0 = g * kBK;
@@ -361,7 +369,7 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
         const bool last_pass = cB == BN;
         uint32_t qa[16], qa2[16];
 #pragma unroll 1
-        for (int s0 = cA + 32 * h; s0 < cB; s0 += 64) {
+        for (int s0 = cA + 32 * h; s0 < cB; s0 += 32 * kGroups) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int c0 = s0 + 16 * q;
@@ -499,6 +507,9 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// epilogue warps of the persistent kernel: 16 unless CAI_TMA_EPI_WARPS=8 (experiments)
+static int tma_epi_warps() { return knobs().tma_epi_warps == 8 ? 8 : 16; }
+
 struct TmaPlan {
   int S, segs, ppx, a_slots, b_slots, ngroups, maxg;
   uint32_t a_slot_bytes, off_a, off_b, off_e, e_bytes, smem;
@@ -506,7 +517,7 @@ struct TmaPlan {
 
 // The single eligibility test (also exported through cai_conv_tma_eligible): geometry the persistent kernel takes,
 // and the shared-memory carve-up it would use.  `kind` as chosen by cai_conv_gemm (1, 2 or 3).
-static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl) {
+static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl, int epi_warps) {
   if (knobs().conv_persist == 0) return false;
   if (kind < 1 || kind > 3) return false;
   if (d->BN != d->Cout || d->BN > 128 || d->BN % 16 || d->Cin % 8) return false;
@@ -544,7 +555,7 @@ static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl
   pl->a_slot_bytes = (2u * a_plane + 127u) & ~127u;
   const uint32_t b_slot = 2u * static_cast<uint32_t>(d->BN) * kBK * 2u;
   const uint32_t gamma = kind == 1 ? static_cast<uint32_t>((d->BN + kBK - 1) / kBK) * b_slot : 0u;
-  const uint32_t slabs = kind == 1 ? 2u * 2u * (kBK / 8) * kLboA : 0u;
+  const uint32_t slabs = kind == 1 ? static_cast<uint32_t>(epi_warps / 4) * 2u * (kBK / 8) * kLboA : 0u;
   // staging: full tile when it fits, else column passes of >= 64 (planes) / 32 (fp32) columns
   uint32_t e_full;
   if (kind == 3)
@@ -605,15 +616,18 @@ int launch_conv_tma(const cai_conv_desc *d, cudaStream_t st) {
   int rc = get_device_props(&dp);
   if (rc != CAI_OK) return rc;
   const int kind = conv_kind(d);
-  const void *fn = kind == 1   ? reinterpret_cast<const void *>(conv_tma_kernel<1>)
-                   : kind == 2 ? reinterpret_cast<const void *>(conv_tma_kernel<2>)
-                               : reinterpret_cast<const void *>(conv_tma_kernel<3>);
   if (kind == 0) return 1;
+  const int ew = tma_epi_warps();
+  const void *fn8[3] = {reinterpret_cast<const void *>(conv_tma_kernel<1, 8>), reinterpret_cast<const void *>(conv_tma_kernel<2, 8>),
+                        reinterpret_cast<const void *>(conv_tma_kernel<3, 8>)};
+  const void *fn16[3] = {reinterpret_cast<const void *>(conv_tma_kernel<1, 16>), reinterpret_cast<const void *>(conv_tma_kernel<2, 16>),
+                         reinterpret_cast<const void *>(conv_tma_kernel<3, 16>)};
+  const void *fn = (ew == 16 ? fn16 : fn8)[kind - 1];
   int max_dyn = 0;
   rc = optin_max_smem(fn, dp, &max_dyn);
   if (rc != CAI_OK) return rc;
   TmaPlan pl;
-  if (!plan_tma(d, kind, max_dyn, &pl)) return 1;
+  if (!plan_tma(d, kind, max_dyn, &pl, ew)) return 1;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return 1;
 
@@ -668,10 +682,19 @@ int launch_conv_tma(const cai_conv_desc *d, cudaStream_t st) {
   }
   for (int g = 0; g < pl.ngroups; ++g) p.glen[g] = d->glen[g];
   const int grid = ntiles < dp.sm_count ? static_cast<int>(ntiles) : dp.sm_count;
-  switch (kind) {
-    case 1: conv_tma_kernel<1><<<grid, kTmaThreads, pl.smem, st>>>(p, maps[0], maps[1]); break;
-    case 2: conv_tma_kernel<2><<<grid, kTmaThreads, pl.smem, st>>>(p, maps[0], maps[1]); break;
-    default: conv_tma_kernel<3><<<grid, kTmaThreads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+  const int threads = ew * 32 + 64;
+  if (ew == 16) {
+    switch (kind) {
+      case 1: conv_tma_kernel<1, 16><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+      case 2: conv_tma_kernel<2, 16><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+      default: conv_tma_kernel<3, 16><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+    }
+  } else {
+    switch (kind) {
+      case 1: conv_tma_kernel<1, 8><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+      case 2: conv_tma_kernel<2, 8><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+      default: conv_tma_kernel<3, 8><<<grid, threads, pl.smem, st>>>(p, maps[0], maps[1]); break;
+    }
   }
   CAI_LAUNCH_CHECK();
   return CAI_OK;
@@ -683,7 +706,7 @@ bool conv_tma_eligible(const cai_conv_desc *d) {
   const int kind = conv_kind(d);
   if (kind == 0 || !encode_tiled_fn()) return false;
   TmaPlan pl;
-  return plan_tma(d, kind, dp.max_smem_optin - 8192, &pl);
+  return plan_tma(d, kind, dp.max_smem_optin - 8192, &pl, tma_epi_warps());
 }
 
 }  // namespace cai

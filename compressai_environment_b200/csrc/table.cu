@@ -92,6 +92,7 @@ const Knobs &knobs() {
     r.coder_lanes = env_int("CAI_CODER_LANES", 0);
     r.conv_persist = env_int("CAI_CONV_PERSIST", -1);
     r.coder_lut_adapt = env_int("CAI_LUT_ADAPT", -1);
+    r.tma_epi_warps = env_int("CAI_TMA_EPI_WARPS", 0);
     return r;
   }();
   return k;

@@ -146,3 +146,88 @@ def pixels_to_u8(x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         check(lib().cai_pixels_f32_to_u8(ptr(x), x.numel(), ptr(out), current_stream()), "cai_pixels_f32_to_u8")
     return out
+
+
+class ArWeights:
+    """Context model + entropy-parameter network of the autoregressive models, laid out for ``cai_ar_encode`` /
+    ``cai_ar_decode`` (row-major fp32 matrices, reduction dimension zero-padded to a multiple of 4; the masked
+    convolution keeps its (k/2)*k + k/2 causal taps in (ky, kx) order with k = tap * M + channel)."""
+
+    def __init__(self, ctx_weight, ctx_bias, convs, slope: float = 0.01):
+        require_cuda(ctx_weight, "context_prediction.weight")
+        n_ctx, M, k, k2 = ctx_weight.shape
+        assert k == k2 and k % 2 == 1 and len(convs) == 3
+        ntaps = (k // 2) * k + k // 2
+        w = ctx_weight.detach().float().permute(0, 2, 3, 1).reshape(n_ctx, k * k * M)[:, :ntaps * M]
+        self.w_ctx, self.b_ctx = w.contiguous(), ctx_bias.detach().float().contiguous()
+        self.mats = []
+        for cw, cb in convs:
+            m = cw.detach().float().reshape(cw.shape[0], -1)
+            kp = (m.shape[1] + 3) // 4 * 4
+            if kp != m.shape[1]:
+                m = torch.nn.functional.pad(m, (0, kp - m.shape[1]))
+            self.mats.append((m.contiguous(), cb.detach().float().contiguous()))
+        self.M, self.n_ctx, self.ksize, self.slope = int(M), int(n_ctx), int(k), float(slope)
+        self.widths = [int(cw.shape[0]) for cw, _ in convs]
+        self.in_width = int(convs[0][0].shape[1])
+
+    def desc(self, params: torch.Tensor, scale_table: torch.Tensor, scale_bound: float, cluster: int = 0, group: int = 0):
+        """``params``: fp32 [B, H, W, P] contiguous (NHWC).  Returns (ArDesc, keep-alive tuple)."""
+        from ._lib import ArDesc
+
+        B, H, W, P = (int(v) for v in params.shape)
+        if P + self.n_ctx != self.in_width:
+            raise ValueError(f"entropy_parameters expects {self.in_width} input channels, got {P} + {self.n_ctx}")
+        tab = scale_table.detach().to(device=params.device, dtype=torch.float32).contiguous()
+        d = ArDesc()
+        d.w_ctx, d.b_ctx = ptr(self.w_ctx), ptr(self.b_ctx)
+        (d.w1, d.b1), (d.w2, d.b2), (d.w3, d.b3) = ((ptr(m), ptr(b)) for m, b in self.mats)
+        d.params, d.scale_table = ptr(params), ptr(tab)
+        d.scale_bound, d.slope = float(scale_bound), self.slope
+        d.T, d.B, d.H, d.W, d.M, d.P, d.n_ctx = int(tab.numel()), B, H, W, self.M, P, self.n_ctx
+        d.n1, d.n2, d.n3 = self.widths
+        d.ksize, d.cluster, d.group = self.ksize, int(cluster), int(group)
+        return d, (tab, params)
+
+
+def ar_encode(weights: ArWeights, y: torch.Tensor, params: torch.Tensor, scale_table, scale_bound: float,
+              cluster: int = 0, group: int = 0):
+    """Encoder scan of the autoregressive models (reference ``_compress_ar``, models/google.py:535-577) for a batch.
+    ``y`` fp32 [B, H, W, M] and ``params`` fp32 [B, H, W, P], both NHWC-contiguous.  Returns (sym, idx) int32
+    [B, H*W*M] in the reference's coding order (pixel-major) and the padded y_hat [B, H+2p, W+2p, M]."""
+    import ctypes
+
+    require_cuda(y)
+    assert y.dtype == torch.float32 and params.dtype == torch.float32 and y.is_contiguous() and params.is_contiguous()
+    B, H, W, M = (int(v) for v in y.shape)
+    p = weights.ksize // 2
+    dev = y.device
+    y_hat = torch.zeros((B, H + 2 * p, W + 2 * p, M), dtype=torch.float32, device=dev)
+    sym = torch.empty((B, H * W * M), dtype=torch.int32, device=dev)
+    idx = torch.empty((B, H * W * M), dtype=torch.int32, device=dev)
+    d, keep = weights.desc(params, scale_table, scale_bound, cluster, group)
+    with torch.cuda.device(dev):
+        check(lib().cai_ar_encode(ctypes.byref(d), ptr(y), ptr(y_hat), ptr(sym), ptr(idx), current_stream()), "cai_ar_encode")
+    return sym, idx, y_hat
+
+
+def ar_decode(weights: ArWeights, table, words: torch.Tensor, word_begin: torch.Tensor, params: torch.Tensor, scale_table,
+              scale_bound: float, cluster: int = 0, group: int = 0, want_symbols: bool = False):
+    """Decoder scan (reference ``_decompress_ar``, models/google.py:620-661): one rANS stream per image, M symbols per
+    latent pixel in raster order.  ``table``: coder.CdfTable; ``words`` / ``word_begin``: the packed strings on the
+    device (coder.strings_to_device).  Returns (padded y_hat [B, H+2p, W+2p, M], status int32 [B], symbols or None)."""
+    import ctypes
+
+    require_cuda(params)
+    assert params.dtype == torch.float32 and params.is_contiguous()
+    B, H, W, _ = (int(v) for v in params.shape)
+    p, M = weights.ksize // 2, weights.M
+    dev = params.device
+    y_hat = torch.zeros((B, H + 2 * p, W + 2 * p, M), dtype=torch.float32, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    sym = torch.empty((B, H * W * M), dtype=torch.int32, device=dev) if want_symbols else None
+    d, keep = weights.desc(params, scale_table, scale_bound, cluster, group)
+    with torch.cuda.device(dev):
+        check(lib().cai_ar_decode(ctypes.byref(d), table.handle, ptr(words), ptr(word_begin), ptr(y_hat), ptr(sym),
+                                  ptr(status), current_stream()), "cai_ar_decode")
+    return y_hat, status, sym

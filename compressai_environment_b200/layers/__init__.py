@@ -1,4 +1,6 @@
 from .gdn import GDN
-from .layers import QReLU
+from .layers import (AttentionBlock, MaskedConv2d, QReLU, ResidualBlock, ResidualBlockUpsample, ResidualBlockWithStride,
+                     conv1x1, conv3x3, subpel_conv3x3)
 
-__all__ = ["GDN", "QReLU"]
+__all__ = ["GDN", "AttentionBlock", "MaskedConv2d", "QReLU", "ResidualBlock", "ResidualBlockUpsample",
+           "ResidualBlockWithStride", "conv1x1", "conv3x3", "subpel_conv3x3"]

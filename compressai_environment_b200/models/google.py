@@ -1,6 +1,7 @@
 """The model classes on the hot path with the reference's interface (compressai/models/google.py):
 ``CompressionModel`` (:56-116), ``FactorizedPrior`` (:119-191), ``ScaleHyperprior`` (:204-321),
-``MeanScaleHyperprior`` (:324-392) and ``get_scale_table`` (:195-201).
+``MeanScaleHyperprior`` (:324-392), ``JointAutoregressiveHierarchicalPriors`` (:395-661) and ``get_scale_table``
+(:195-201).
 
 Same constructor arguments, submodule names (``g_a``, ``g_s``, ``h_a``, ``h_s``, ``entropy_bottleneck``,
 ``gaussian_conditional``) and ``state_dict`` keys, same return dictionaries.  Differences underneath:
@@ -20,8 +21,8 @@ import torch.nn as nn
 
 from .. import _cache, _lib, coder, kernels
 from ..entropy_models import EntropyBottleneck, GaussianConditional
-from ..layers import GDN
-from ..transforms import TransformStack
+from ..layers import GDN, MaskedConv2d
+from ..transforms import Conv2d, TransformStack
 from .utils import conv, deconv, update_registered_buffers
 
 __all__ = [
@@ -29,6 +30,7 @@ __all__ = [
     "FactorizedPrior",
     "ScaleHyperprior",
     "MeanScaleHyperprior",
+    "JointAutoregressiveHierarchicalPriors",
     "get_scale_table",
     "SCALES_MIN",
     "SCALES_MAX",
@@ -458,3 +460,115 @@ class MeanScaleHyperprior(ScaleHyperprior):
         gaussian_params = self.h_s(z_hat)
         scales_hat, means_hat = gaussian_params.chunk(2, 1)
         return scales_hat, means_hat
+
+
+class JointAutoregressiveHierarchicalPriors(MeanScaleHyperprior):
+    r"""Joint autoregressive + hierarchical priors model (Minnen et al., NeurIPS 2018); reference
+    models/google.py:395-661.  Same submodules and ``state_dict`` keys (``context_prediction`` is a ``MaskedConv2d``,
+    ``entropy_parameters`` three 1x1 convolutions).
+
+    ``compress`` / ``decompress``: the reference walks the latent grid pixel by pixel in Python on the CPU
+    (``_compress_ar`` :535-577, ``_decompress_ar`` :620-661).  Here the whole scan of a batch is ONE persistent kernel
+    launch (csrc/ar.cu: a thread-block cluster per image group, weights streamed from L2, the image's rANS chain decoded
+    in the loop); the encoder's symbols / indexes are then coded by the batched rANS kernel, one string per image, in
+    the reference's order (pixel-major, channel-minor), so the strings have the reference's format."""
+
+    def __init__(self, N=192, M=192, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.g_a = TransformStack(conv(3, N, kernel_size=5, stride=2), GDN(N), conv(N, N, kernel_size=5, stride=2), GDN(N),
+                                 conv(N, N, kernel_size=5, stride=2), GDN(N), conv(N, M, kernel_size=5, stride=2))
+        self.g_s = TransformStack(deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                                 deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                                 deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                                 deconv(N, 3, kernel_size=5, stride=2))
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True),
+                                 conv(N, N, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 conv(N, N, stride=2, kernel_size=5))
+        self.h_s = TransformStack(deconv(N, M, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 deconv(M, M * 3 // 2, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                 conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+        self.entropy_parameters = TransformStack(
+            Conv2d(M * 12 // 3, M * 10 // 3, kernel_size=1, stride=1, padding=0), nn.LeakyReLU(inplace=True),
+            Conv2d(M * 10 // 3, M * 8 // 3, kernel_size=1, stride=1, padding=0), nn.LeakyReLU(inplace=True),
+            Conv2d(M * 8 // 3, M * 6 // 3, kernel_size=1, stride=1, padding=0))
+        self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.N = int(N)
+        self.M = int(M)
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
+
+    def forward(self, x):
+        y = self.g_a(_nhwc(x))
+        z = self.h_a(y)
+        z_hat, z_likelihoods = self.entropy_bottleneck(z)
+        params = self.h_s(z_hat)
+        y_hat = self.gaussian_conditional.quantize(y, "noise" if self.training else "dequantize")
+        ctx_params = self.context_prediction(y_hat)
+        gaussian_params = self.entropy_parameters(torch.cat((params, ctx_params), dim=1))
+        scales_hat, means_hat = gaussian_params.chunk(2, 1)
+        _, y_likelihoods = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods, "z": z_likelihoods}}
+
+    # launch shape of the scan (0 = automatic): CTAs per cluster, images per cluster
+    ar_cluster = 0
+    ar_group = 0
+
+    def _ar_weights(self) -> kernels.ArWeights:
+        cp, ep = self.context_prediction, self.entropy_parameters
+        convs = [ep[0], ep[2], ep[4]]
+        tensors = [cp.weight, cp.bias, cp.mask] + [t for c in convs for t in (c.weight, c.bias)]
+
+        def build():
+            return kernels.ArWeights(cp.weight.detach() * cp.mask, cp.bias, [(c.weight, c.bias) for c in convs],
+                                     slope=float(ep[1].negative_slope))
+
+        return _cache.cached(self, "ar_weights", _cache.tensor_key(*tensors), build, cp.weight.device)
+
+    @staticmethod
+    def _to_nhwc(t):
+        return t.permute(0, 2, 3, 1).contiguous()
+
+    @torch.no_grad()
+    def compress(self, x):
+        self._check_tables()
+        if not x.is_cuda:
+            x = x.to(self.gaussian_conditional._quantized_cdf.device)
+        if x.dtype == torch.uint8:
+            x = kernels.pixels_to_float(x)
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = self.g_a(_nhwc(x))
+        z = self.h_a(y)
+        z_sym, z_idx = kernels.eb_quantize_index(z, eb._get_medians())
+        z_enc = coder.encode(eb._table(), z_sym, z_idx)
+        z_hat = kernels.dequantize(z_sym, None, eb._get_medians(), tuple(z.shape), _CL)
+        params = self.h_s(z_hat)
+        if params.shape[-2:] != y.shape[-2:]:
+            raise ValueError("the image size must be a multiple of 64 (latent and hyper-synthesis grids differ)")
+        sym, idx, _ = kernels.ar_encode(self._ar_weights(), self._to_nhwc(y), self._to_nhwc(params), gc.scale_table,
+                                        gc._bound_scale(), self.ar_cluster, self.ar_group)
+        y_enc = coder.encode(gc._table(), sym, idx)
+        y_strings, z_strings = coder.batches_to_bytes([y_enc, z_enc])
+        coder.check_status([y_enc.status, z_enc.status], "rANS encode")
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        self._check_tables()
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        dev = gc._quantized_cdf.device
+        _lib.require_cuda(gc._quantized_cdf, "model buffers")
+        z_hat = eb.decompress(strings[1], shape, memory_format=_CL)
+        params = self.h_s(z_hat)
+        words, wb, keep = coder.strings_to_device(coder.as_strings(strings[0]), dev)
+        y_hat, status, _ = kernels.ar_decode(self._ar_weights(), gc._table(), words, wb, self._to_nhwc(params),
+                                             gc.scale_table, gc._bound_scale(), self.ar_cluster, self.ar_group)
+        coder.check_status([status], "rANS decode")
+        p = self.context_prediction.kernel_size // 2
+        y_hat = y_hat[:, p:-p, p:-p, :].permute(0, 3, 1, 2)
+        x_hat = self.g_s(y_hat, clamp=(0.0, 1.0), nchw_out=True)
+        return {"x_hat": x_hat}

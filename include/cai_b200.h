@@ -324,6 +324,39 @@ int cai_gdn_bwd_finish(const float *p, const float *x, const float *u, int32_t i
 int cai_gdn_bwd_params(const float *t, const float *x, int64_t P, int32_t C, int32_t inverse, float *g_beta,
                        float *g_gamma, cai_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Autoregressive context model scan (csrc/ar.cu), replacing the per-pixel Python loops of
+ * JointAutoregressiveHierarchicalPriors._compress_ar / _decompress_ar (compressai/models/google.py:535-577,
+ * :620-661; inherited by the Cheng2020 models, compressai/models/waseda.py:44-153).  Per latent pixel, in raster order:
+ *   ctx = context_prediction (MaskedConv2d type "A", layers.py:52-78) on the ksize x ksize crop of y_hat
+ *   (scales | means) = entropy_parameters(cat(params, ctx))   -- three 1x1 convolutions, LeakyReLU(slope) between
+ *   idx = GaussianConditional.build_indexes(scales)
+ *   encoder: sym = int32(rint(y - means)), y_hat = sym + means            (symbols / indexes coded afterwards by
+ *                                                                          cai_rans_encode_batch, one string per image)
+ *   decoder: sym = M symbols from the image's rANS stream (RansDecoder::set_stream / decode_stream,
+ *            rans_interface.cpp:286-359), y_hat = sym + means
+ * All tensors fp32 NHWC on the device.  Weight matrices are row-major [rows][K padded to a multiple of 4 with zeros]:
+ *   w_ctx [n_ctx][ntaps * M]   the ntaps = (ksize/2) * ksize + ksize/2 unmasked taps in (ky, kx) order, k = tap * M + c
+ *   w1 [n1][pad4(P + n_ctx)], w2 [n2][pad4(n1)], w3 [n3 = 2 M][pad4(n2)]
+ * y_hat: [B, H + 2 (ksize/2), W + 2 (ksize/2), M] with a zero border (the decoder needs it zero-initialised).
+ * sym / idx: int32 [B, H * W * M], pixel-major and channel-minor -- the order in which the reference pushes them.
+ * One thread-block cluster of `cluster` CTAs (0 = 8) scans `group` images (0 = automatic); a row of a layer is always
+ * summed in the same order, so encoder and decoder obtain bit-identical parameters whatever the launch shape.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cai_ar_desc {
+  const float *w_ctx, *b_ctx, *w1, *b1, *w2, *b2, *w3, *b3;
+  const float *params;       /* [B, H, W, P]: hyper-synthesis output */
+  const float *scale_table;  /* [T] */
+  float scale_bound, slope;
+  int32_t T, B, H, W, M, P, n_ctx, n1, n2, n3, ksize;
+  int32_t cluster, group;
+} cai_ar_desc;
+
+int cai_ar_encode(const cai_ar_desc *d, const float *y, float *y_hat, int32_t *sym, int32_t *idx, cai_stream_t stream);
+/* words / word_begin [B + 1]: the packed strings as in cai_rans_decode_batch; sym may be NULL; status int32 [B] */
+int cai_ar_decode(const cai_ar_desc *d, cai_table_t t, const uint32_t *words, const int64_t *word_begin, float *y_hat,
+                  int32_t *sym, int32_t *status, cai_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

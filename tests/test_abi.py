@@ -83,6 +83,26 @@ def test_conv_desc_layout_matches_header(tmp_path):
         assert getattr(ConvDesc, "is_" if f == "is" else f).offset == off, f
 
 
+def test_ar_desc_layout_matches_header(tmp_path):
+    """Same check for the ctypes mirror of cai_ar_desc."""
+    import ctypes, subprocess
+
+    from compressai_environment_b200._lib import ArDesc
+
+    fields = [n for n, _ in ArDesc._fields_]
+    src = tmp_path / "layout_ar.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cai_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(cai_ar_desc));\n'
+                   + "".join(f'  printf(" %zu", offsetof(cai_ar_desc, {f}));\n' for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout_ar"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got[0] == ctypes.sizeof(ArDesc)
+    for f, off in zip(fields, got[1:]):
+        assert getattr(ArDesc, f).offset == off, f
+
+
 def test_interval_union():
     sys.path.insert(0, ROOT)
     import bench
