@@ -894,7 +894,7 @@ def other_configs(dev):
     one request at a time: MP/s = image pixels / (compress + decompress wall time), as eval_model times it."""
     import torch
 
-    from compressai_environment_b200.zoo import bmshj2018_factorized, mbt2018_mean
+    from compressai_environment_b200.zoo import bmshj2018_factorized, mbt2018, mbt2018_mean
 
     out = {}
 
@@ -941,6 +941,24 @@ def other_configs(dev):
                                                  "bpp": nb * 8 / (2176 * 3840), "gain_y": 64.0, "gain_s": 64.0,
                                                  "requests_in_flight": 1,
                                                  "note": "one 10.4 M-symbol y string: a single serial rANS chain"}
+        del net, x
+        # the autoregressive model (per-pixel context model; csrc/ar.cu scans the whole batch in
+        # one cluster-kernel launch per direction).  The reference runs this loop in Python on the CPU:
+        # tools/ar_bench.py --ref times it on the same box (4.3 s to decode ONE image on 16 cores).
+        torch.manual_seed(0)
+        net = mbt2018(3)
+        with torch.no_grad():
+            for m, g in ((net.g_a[6], 40.0), (net.entropy_parameters[4], 8.0)):
+                m.weight.mul_(g)
+                m.bias.mul_(g)
+        net = net.to(dev).eval()
+        net.update(force=True)
+        x = make_images(16).to(dev)
+        dt, nb = run(net, x, 3)
+        out["AR_mbt2018_q3_16x768x512"] = {"value": 16 * H * W / 1e6 / dt, "unit": UNIT, "ms_per_batch": dt * 1e3,
+                                           "bpp": nb * 8 / (16 * H * W), "gain_y": 40.0, "requests_in_flight": 1,
+                                           "note": "JointAutoregressiveHierarchicalPriors: sequential context model, "
+                                                   "one string per image, round trip checked in tests/test_ar_gpu.py"}
         del net, x
         torch.cuda.empty_cache()
     except Exception as e:  # secondary figures never take the headline down
