@@ -802,7 +802,7 @@ def ours(args, rank, world):
                            "tensors of the reference API move 4x the PCIe bytes and at 8 GPUs are bounded by the "
                            "box's shared host<->device bandwidth (profiles/r02_pcie_probe_8gpu.txt)"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv / deconv / fused GDN)", "bound": "tensor",
+        "roofline": {"kernel": "conv_gemm_kernel + conv_tma_kernel (tcgen05 implicit GEMM: conv / deconv / fused GDN; per-tile and persistent TMA-fed variants)", "bound": "tensor",
                      "achieved": conv_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (conv_tf / tpeak) if conv_tf else None,
                      "traffic": traffic, "traffic_unit": f"DRAM bytes per launch (ncu, profiles/{traffic_src})",
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else
