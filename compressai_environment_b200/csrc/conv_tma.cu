@@ -31,9 +31,12 @@
 
 namespace cai {
 
-// Epilogue warps per CTA: template parameter EW = 8 or 16 (EW / 4 "groups" per TMEM lane quarter; group h takes every
-// (EW/4)-th 32-column slab and owns x^2 slab buffer h).  The epilogue of the short-K layers is bound by instruction issue
-// with few warps per scheduler (ncu r02: 0.39 IPC per sub-partition with 8 warps): 16 warps double the issue supply.
+// Epilogue warps per CTA: template parameter EW = 8 or 16 = one or two TEAMS of 8 warps.  A team drains one tile: two
+// groups of 128 threads (thread = TMEM lane = pixel row; group h takes alternate 32-column slabs and owns one x^2 slab
+// buffer).  A tile's epilogue is a dependent chain (x^2 slabs -> norm GEMM -> output math -> staging -> copy-out, with
+// two named barriers): more warps on ONE tile do not shorten it (measured: 16 warps on one tile 1.273 ms vs 8 warps
+// 1.295 ms for the first layer), so with EW = 16 the two teams take ALTERNATE tiles -- team t owns accumulator set t,
+// slab buffers 2t / 2t+1, staging region t and named barrier 1 + t -- and one team's waits overlap the other's stores.
 // Two more warps follow: warp EW = TMA producer, warp EW + 1 = MMA issuer (owns TMEM).
 constexpr int kTmaMaxGroups = 4;
 constexpr int kMaxRing = 8;
@@ -88,10 +91,11 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
   __shared__ __align__(8) uint64_t acc_full[2], acc_free[2], slab_full[kTmaMaxGroups], slab_free[kTmaMaxGroups], norm_full[2], gamma_bar;
   constexpr int kTmaEpiWarps = EW;
   constexpr int kTmaEpiThreads = EW * 32;
-  constexpr int kGroups = EW / 4;
-  static_assert(kGroups >= 1 && kGroups <= kTmaMaxGroups && (kGroups & (kGroups - 1)) == 0, "EW must be 4, 8 or 16");
+  constexpr int kTeams = EW / 8;
+  constexpr int kGroups = 2 * kTeams;  // slab buffers: two per team
+  static_assert(kTeams == 1 || kTeams == 2, "EW must be 8 or 16");
   __shared__ uint32_t s_tmem_base;
-  __shared__ int64_t s_opix[kBM];
+  __shared__ int64_t s_opix[2][kBM];
   __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) float s_beta[128];
 
@@ -215,7 +219,8 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
       uint32_t g_use[kGroups] = {};  // completed uses of each slab buffer (phase of slab_full)
       auto gdn_issue = [&](bool block) {
         while (g_next < gk) {
-          const int buf = g_next & (kGroups - 1);
+          const int gteam = (kTeams == 2) ? g_set : 0;  // the pending tile's team = its accumulator set
+          const int buf = 2 * gteam + (g_next & 1);
           if (block) mbar_wait_bounded(&slab_full[buf], g_use[buf] & 1);
           else if (!mbar_test(&slab_full[buf], g_use[buf] & 1)) return;
           tc_fence_after();
@@ -223,7 +228,8 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
             mbar_wait_bounded(&gamma_bar, 0);  // immediate after the first tile
           }
           const uint32_t d_norm = tmem_base + static_cast<uint32_t>(g_set) * set_cols + acc_cols;
-          const uint32_t sl = smem_u32(sm_e) + static_cast<uint32_t>(buf) * (2u * slab_plane);
+          const uint32_t sl = smem_u32(sm_e) + static_cast<uint32_t>(gteam) * p.e_bytes +
+                              static_cast<uint32_t>(g_next & 1) * (2u * slab_plane);
           const uint32_t gb = smem_u32(sm_gamma) + static_cast<uint32_t>(g_next) * (2u * b_plane);
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
@@ -244,7 +250,18 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int set = it & 1;
         if (it >= 2) {  // the epilogue of tile it - 2 must have drained this accumulator set
-          mbar_wait_bounded(&acc_free[set], ((it >> 1) - 1) & 1);
+          const uint32_t par = static_cast<uint32_t>((it >> 1) - 1) & 1u;
+          if (kGdn) {
+            // keep serving the OTHER team's norm GEMM while this team finishes its output phase: blocking here would
+            // chain the two teams' epilogues through this thread (measured: two teams then gain only 7 %)
+            uint32_t spins = 0;
+            while (!mbar_test(&acc_free[set], par)) {
+              gdn_issue(false);
+              if (++spins > kSpinLimit) spin_fail();
+            }
+          } else {
+            mbar_wait_bounded(&acc_free[set], par);
+          }
           tc_fence_after();
         }
         const uint32_t d_main = tmem_base + static_cast<uint32_t>(set) * set_cols;
@@ -295,8 +312,13 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps: thread = TMEM lane = pixel row r, group h takes alternate slabs ==========
-    const int r = tid & (kBM - 1);
-    const int h = tid >> 7;
+    const int team = (kTeams == 2) ? (tid >> 8) : 0;
+    const int tt = tid & 255;  // thread within the team
+    const int r = tt & (kBM - 1);
+    const int h = tt >> 7;
+    const int sbuf = 2 * team + h;  // this group's x^2 slab buffer
+    unsigned char *sm_et = sm_e + static_cast<uint32_t>(team) * p.e_bytes;  // the team's slab / staging region
+    int64_t *opix_t = s_opix[team];
     const uint32_t lane_base = (static_cast<uint32_t>(warp & 3) * 32u) << 16;
     const uint32_t row_off = (static_cast<uint32_t>(r) >> 3) * 128u + (static_cast<uint32_t>(r) & 7u) * 16u;
     const int epi = kGdn ? 0 : p.epilogue;
@@ -309,8 +331,9 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
     const uint32_t pitch_f = ncols * 4u + 16u, pitch_b = ncols * 2u + 16u;
     const uint32_t off_out = kF32 ? kBM * pitch_f : 0u;  // first plane pair (out planes, or |out| planes for KIND 3)
     uint32_t slab_uses = 0;  // times this group has filled its slab buffer (buffer index = h)
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    int it = team;  // team t drains the tiles it = t, t + kTeams, ... of this CTA's sequence
+    for (int tile = blockIdx.x + team * static_cast<int>(gridDim.x); tile < p.ntiles;
+         tile += kTeams * static_cast<int>(gridDim.x), it += kTeams) {
       const int set = it & 1;
       const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
       const int seg = tile % per_row;
@@ -327,9 +350,9 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
         // x = acc + bias; x^2 split into bf16 planes -> slab buffer h, one 32-column slab per GDN k-step
         uint32_t raw[32];
 #pragma unroll 1
-        for (int g = h; g < gk; g += kGroups) {
-          if (slab_uses > 0) mbar_wait_bounded(&slab_free[h], (slab_uses - 1) & 1);
-          unsigned char *sl = sm_e + static_cast<uint32_t>(h) * (2u * slab_plane);
+        for (int g = h; g < gk; g += 2) {
+          if (slab_uses > 0) mbar_wait_bounded(&slab_free[sbuf], (slab_uses - 1) & 1);
+          unsigned char *sl = sm_et + static_cast<uint32_t>(h) * (2u * slab_plane);
           const int col0 = g * kBK;
           tmem_ld32_nowait(t_main + static_cast<uint32_t>(col0), raw);
           tmem_wait_ld();
@@ -356,20 +379,20 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
             *reinterpret_cast<uint4 *>(sl + slab_plane + so) = vl;
           }
           fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(&slab_full[h]);
+          mbar_arrive(&slab_full[sbuf]);
           ++slab_uses;
         }
         mbar_wait_bounded(&norm_full[set], use_par);
         tc_fence_after();
       }
-      if (h == 0) s_opix[r] = opix;
+      if (h == 0) opix_t[r] = opix;
       // ---- output: TMEM -> registers -> math -> staging (thread = row), then cooperative full-line copy-out
       for (int cA = 0; cA < BN; cA += ncols) {
         const int cB = (cA + ncols < BN) ? cA + ncols : BN;
         const bool last_pass = cB == BN;
         uint32_t qa[16], qa2[16];
 #pragma unroll 1
-        for (int s0 = cA + 32 * h; s0 < cB; s0 += 32 * kGroups) {
+        for (int s0 = cA + 32 * h; s0 < cB; s0 += 64) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int c0 = s0 + 16 * q;
@@ -417,7 +440,7 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
             }
             const uint32_t cc = static_cast<uint32_t>(c0 - cA);
             if (kF32) {
-              float4 *o = reinterpret_cast<float4 *>(sm_e + static_cast<uint32_t>(r) * pitch_f + cc * 4u);
+              float4 *o = reinterpret_cast<float4 *>(sm_et + static_cast<uint32_t>(r) * pitch_f + cc * 4u);
 #pragma unroll
               for (int w4 = 0; w4 < 4; ++w4) o[w4] = make_float4(v[4 * w4], v[4 * w4 + 1], v[4 * w4 + 2], v[4 * w4 + 3]);
             }
@@ -426,8 +449,8 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 const Pack8 pk = split8(v + 8 * hh);
-                *reinterpret_cast<uint4 *>(sm_e + off_out + rb + hh * 16u) = pk.hi;
-                *reinterpret_cast<uint4 *>(sm_e + off_out + kBM * pitch_b + rb + hh * 16u) = pk.lo;
+                *reinterpret_cast<uint4 *>(sm_et + off_out + rb + hh * 16u) = pk.hi;
+                *reinterpret_cast<uint4 *>(sm_et + off_out + kBM * pitch_b + rb + hh * 16u) = pk.lo;
               }
             } else if (has_abs) {
               float sv[16];
@@ -436,15 +459,15 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 const Pack8 pk = split8(sv + 8 * hh);
-                *reinterpret_cast<uint4 *>(sm_e + off_out + rb + hh * 16u) = pk.hi;
-                *reinterpret_cast<uint4 *>(sm_e + off_out + kBM * pitch_b + rb + hh * 16u) = pk.lo;
+                *reinterpret_cast<uint4 *>(sm_et + off_out + rb + hh * 16u) = pk.hi;
+                *reinterpret_cast<uint4 *>(sm_et + off_out + kBM * pitch_b + rb + hh * 16u) = pk.lo;
               }
             }
           }
         }
         if (last_pass) tc_fence_before();  // last TMEM reads of this accumulator set
-        asm volatile("bar.sync 1, %0;" ::"n"(kTmaEpiThreads) : "memory");
-        if (last_pass && tid == 0) mbar_arrive(&acc_free[set]);  // tile it + 2 may overwrite the set
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+        if (last_pass && tt == 0) mbar_arrive(&acc_free[set]);  // tile it + 2 may overwrite the set
         // ---- cooperative copy-out: 16-byte units, consecutive lanes along a row (full-line stores)
         const int cols_here = (cB - cA < p.Cout - cA) ? (cB - cA) : (p.Cout - cA);
         if (cols_here > 0) {
@@ -469,16 +492,16 @@ conv_tma_kernel(const __grid_constant__ TmaConvParams p, const __grid_constant__
             unsigned char *gbase = gptr + static_cast<int64_t>(cA) * esize;
             const int64_t row_stride = static_cast<int64_t>(p.Cout) * esize;
             const uint32_t total_u = kBM * units;
-            for (uint32_t u = tid; u < total_u; u += static_cast<uint32_t>(kTmaEpiThreads)) {
+            for (uint32_t u = tt; u < total_u; u += 256u) {
               const uint32_t row = u / units, jj = u - row * units;
-              const int64_t op = s_opix[row];
+              const int64_t op = opix_t[row];
               if (op < 0) continue;
-              const uint4 val = *reinterpret_cast<const uint4 *>(sm_e + soff + row * pitch + jj * 16u);
+              const uint4 val = *reinterpret_cast<const uint4 *>(sm_et + soff + row * pitch + jj * 16u);
               *reinterpret_cast<uint4 *>(gbase + op * row_stride + jj * 16u) = val;
             }
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kTmaEpiThreads) : "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
       }
     }
   }
@@ -555,7 +578,8 @@ static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl
   pl->a_slot_bytes = (2u * a_plane + 127u) & ~127u;
   const uint32_t b_slot = 2u * static_cast<uint32_t>(d->BN) * kBK * 2u;
   const uint32_t gamma = kind == 1 ? static_cast<uint32_t>((d->BN + kBK - 1) / kBK) * b_slot : 0u;
-  const uint32_t slabs = kind == 1 ? static_cast<uint32_t>(epi_warps / 4) * 2u * (kBK / 8) * kLboA : 0u;
+  const uint32_t teams = static_cast<uint32_t>(epi_warps / 8);  // each team has its own slab / staging region
+  const uint32_t slabs = kind == 1 ? 2u * 2u * (kBK / 8) * kLboA : 0u;
   // staging: full tile when it fits, else column passes of >= 64 (planes) / 32 (fp32) columns
   uint32_t e_full;
   if (kind == 3)
@@ -570,8 +594,8 @@ static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl
   for (uint32_t e_bytes : {e_full, e_min}) {
     uint32_t eb = e_bytes > slabs ? e_bytes : slabs;
     eb = (eb + 127u) & ~127u;
-    if (gamma + eb + 2u * pl->a_slot_bytes + 3u * b_slot > budget) continue;
-    uint32_t rest = budget - gamma - eb;
+    if (gamma + teams * eb + 2u * pl->a_slot_bytes + 3u * b_slot > budget) continue;
+    uint32_t rest = budget - gamma - teams * eb;
     int a_slots = 2, b_slots = 3;
     rest -= 2u * pl->a_slot_bytes + 3u * b_slot;
     // grow the weight ring first (one slab per tap: the finest-grained consumer), then the row ring
@@ -595,7 +619,7 @@ static bool plan_tma(const cai_conv_desc *d, int kind, int max_smem, TmaPlan *pl
     pl->off_b = pl->off_a + static_cast<uint32_t>(a_slots) * pl->a_slot_bytes;
     pl->off_e = pl->off_b + static_cast<uint32_t>(b_slots) * b_slot;
     pl->e_bytes = eb;
-    pl->smem = pl->off_e + eb;
+    pl->smem = pl->off_e + teams * eb;
     return pl->smem <= static_cast<uint32_t>(max_smem);
   }
   return false;

@@ -1,3 +1,5 @@
 O=gpurun_out
-for k in conv deconv; do for d in 0 1 2 3 4; do echo "== $k debug=$d"; CAI_CONV_DEBUG=$d python tools/conv_probe.py 32 $k 2>&1 | tail -1; done; done > $O/ablate_r02.txt 2>&1
-cat $O/ablate_r02.txt
+timeout 900 python -m pytest tests/test_conv_tma_gpu.py tests/test_transforms_gpu.py -m gpu -x -q > $O/t_teams.log 2>&1; echo "tests rc=$?"
+tail -3 $O/t_teams.log | cut -c1-300
+python tools/layer_times.py 32 5 > $O/lt_teams2b.txt 2>&1
+grep -E "tma|total|stack" $O/lt_teams2b.txt
