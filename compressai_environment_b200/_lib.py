@@ -47,7 +47,7 @@ class ArDesc(Structure):
     _fields_ = ([(n, c_void_p) for n in ("w_ctx", "b_ctx", "w1", "b1", "w2", "b2", "w3", "b3", "params", "scale_table")]
                 + [("scale_bound", c_float), ("slope", c_float)]
                 + [(n, c_int32) for n in ("T", "B", "H", "W", "M", "P", "n_ctx", "n1", "n2", "n3", "ksize", "cluster",
-                                          "group")])
+                                          "group", "flags")])
 
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/cai_b200.h

@@ -51,7 +51,8 @@ struct ArKernelParams {
   const int64_t *word_begin;  // [B + 1]
   int32_t *status;            // [B]
   float bound, slope;
-  uint32_t enc_bytes;
+  uint32_t enc_bytes;    // header + row metadata + CDF rows of the blob
+  uint32_t stage_bytes;  // what the decoder stages: enc_bytes, or the whole blob (with the decode LUT) when it fits
   int T, B, H, W, M, P, n_ctx, n1, n2, n3, ksize, pad;
   int K0, K1p, K2p, K3p;  // padded reduction lengths (multiples of 4)
   int R;
@@ -170,30 +171,73 @@ struct ArDec {
   }
 };
 
-// One symbol with CDF row `k`; `meta` / `cdf` are the shared-memory copies of the packed table.
-__device__ __forceinline__ int32_t ar_decode_symbol(ArDec &d, const RowMeta *meta, const uint16_t *cdf, int k) {
-  const RowMeta m = meta[k];
+// One symbol with CDF row metadata `m`; `cdf` / `lut` are the shared-memory copies of the packed table.  With the
+// decode LUT staged (lut != nullptr; same entry format as rans.cu: {start | freq << 16, s0}, freq == 0 = "search forward
+// from s0" or, with bit 31 of the second word, "whole bucket inside the escape symbol") the common symbol costs one
+// LDS; without it the row is searched 32 ways at a time.
+__device__ __forceinline__ int32_t ar_decode_symbol(ArDec &d, const RowMeta m, const uint16_t *cdf, const uint2 *lut,
+                                                    int lut_shift) {
   const uint16_t *row = cdf + m.cdf_off;
   const uint32_t cf = static_cast<uint32_t>(d.x) & 0xffffu;
-  // s = #{ j < len - 1 : row[j] <= cf } - 1  (row[0] = 0; the terminal 65536 is stored as 0 and never compared)
-  int lo = 0, cnt = m.len - 1;
-  while (cnt > 32) {
-    const int stride = (cnt + 31) >> 5;
-    const int off = d.lane * stride;
-    const bool le = off < cnt && row[lo + off] <= cf;
-    const int c = __popc(__ballot_sync(0xffffffffu, le));  // >= 1: row[lo] <= cf by induction
-    lo += (c - 1) * stride;
-    cnt = min(stride, cnt - (c - 1) * stride);
+  const int32_t max_value = m.len - 2;
+  int s;
+  uint32_t start, freq;
+  if (lut != nullptr) {
+    const uint2 e = lut[m.lut_off + (cf >> lut_shift)];
+    start = e.x & 0xffffu;
+    freq = e.x >> 16;
+    s = static_cast<int>(e.y);
+    if (freq == 0u && (e.y & 0x80000000u)) {
+      s = max_value;
+      start = e.y & 0xffffu;
+      freq = 0x10000u - start;
+    } else if (freq == 0u) {
+      for (;;) {  // lane i tests symbol s + i; exactly one lane can hit
+        const int cand = s + d.lane;
+        uint32_t packed = 0;
+        if (cand <= max_value) {
+          const uint32_t c_lo = row[cand];
+          const uint32_t c_hi = (cand == max_value) ? 0x10000u : static_cast<uint32_t>(row[cand + 1]);
+          if (c_lo <= cf && cf < c_hi) packed = ((c_hi - c_lo) << 16) | c_lo;
+        }
+        const uint32_t hit = __ballot_sync(0xffffffffu, packed != 0u);
+        if (hit) {
+          const int src = __ffs(hit) - 1;
+          packed = __shfl_sync(0xffffffffu, packed, src);
+          s += src;
+          start = packed & 0xffffu;
+          freq = packed >> 16;
+          break;
+        }
+        s += 32;
+        if (s > max_value) {  // malformed table: stay in bounds, keep the chain defined
+          s = max_value < 0 ? 0 : max_value;
+          start = row[s];
+          freq = 1u;
+          break;
+        }
+      }
+    }
+  } else {
+    // s = #{ j < len - 1 : row[j] <= cf } - 1  (row[0] = 0; the terminal 65536 is stored as 0 and never compared)
+    int lo = 0, cnt = m.len - 1;
+    while (cnt > 32) {
+      const int stride = (cnt + 31) >> 5;
+      const int off = d.lane * stride;
+      const bool le = off < cnt && row[lo + off] <= cf;
+      const int c = __popc(__ballot_sync(0xffffffffu, le));  // >= 1: row[lo] <= cf by induction
+      lo += (c - 1) * stride;
+      cnt = min(stride, cnt - (c - 1) * stride);
+    }
+    const bool le = d.lane < cnt && row[lo + d.lane] <= cf;
+    s = lo + __popc(__ballot_sync(0xffffffffu, le)) - 1;
+    start = row[s];
+    freq = (static_cast<uint32_t>(row[s + 1]) - start) & 0xffffu;
+    if (freq == 0u) freq = 65536u;
   }
-  const bool le = d.lane < cnt && row[lo + d.lane] <= cf;
-  const int s = lo + __popc(__ballot_sync(0xffffffffu, le)) - 1;
-  const uint32_t start = row[s];
-  uint32_t freq = (static_cast<uint32_t>(row[s + 1]) - start) & 0xffffu;
-  if (freq == 0) freq = 65536u;
   d.x = static_cast<uint64_t>(freq) * (d.x >> 16) + cf - start;
   d.renorm();
   int32_t value = s;
-  const int32_t max_value = m.len - 2;
   if (value == max_value) {  // bypass-coded tail (rans_interface.cpp:256-279)
     uint32_t val = d.get_bits4();
     int32_t nb = static_cast<int32_t>(val);
@@ -240,11 +284,17 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_scan_kernel(const ArKernelPa
   for (int i = tid; i < p.T; i += kArThreads) s_tab[i] = p.scale_table[i];
   const RowMeta *meta = nullptr;
   const uint16_t *cdf = nullptr;
+  const uint2 *lut = nullptr;  // staged only when the whole blob fits beside the activation vectors (p.stage_bytes)
+  int lut_shift = 0;
   if (kDecode) {
-    stage_blob(s_blob, p.blob, p.enc_bytes, &s_bar);
+    stage_blob(s_blob, p.blob, p.stage_bytes, &s_bar);
     const BlobHeader *hdr = reinterpret_cast<const BlobHeader *>(s_blob);
     meta = reinterpret_cast<const RowMeta *>(s_blob + hdr->off_meta);
     cdf = reinterpret_cast<const uint16_t *>(s_blob + hdr->off_cdf);
+    if (p.stage_bytes > p.enc_bytes) {
+      lut = reinterpret_cast<const uint2 *>(s_blob + hdr->off_lut);
+      lut_shift = hdr->lut_shift;
+    }
   }
   const int my_b = b0 + rank;  // image owned by this CTA (if rank < G and inside the batch)
   const bool owner = rank < G && my_b < p.B;
@@ -302,8 +352,11 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_scan_kernel(const ArKernelPa
           for (int c = tid; c < p.M; c += kArThreads) s_idx[c] = ar_index_of(mine[c], p.bound, s_tab, p.T);
           __syncthreads();
           if (warp == 0) {
+            RowMeta m_next = meta[s_idx[0]];
             for (int c = 0; c < p.M; ++c) {
-              const int32_t s = ar_decode_symbol(dec, meta, cdf, s_idx[c]);
+              const RowMeta m = m_next;
+              if (c + 1 < p.M) m_next = meta[s_idx[c + 1]];  // off the chain: next symbol's row while this one decodes
+              const int32_t s = ar_decode_symbol(dec, m, cdf, lut, lut_shift);
               if (lane == 0) s_sym[c] = s;
             }
           }
@@ -348,7 +401,7 @@ static int launch_ar(const ArKernelParams &p, size_t smem, cudaStream_t stream, 
 static size_t ar_smem_bytes(const ArKernelParams &p, int G, bool decode) {
   size_t fl = static_cast<size_t>(G) * (p.K0 + p.K1p + p.K2p + p.K3p + pad4(p.n3)) + pad4(p.T) + 2 * pad4(p.M);
   size_t bytes = fl * 4;
-  if (decode) bytes += (p.enc_bytes + 15u) & ~15u;
+  if (decode) bytes += (p.stage_bytes + 15u) & ~15u;
   return bytes;
 }
 
@@ -385,6 +438,7 @@ static int ar_run(const cai_ar_desc *d, bool decode, cai_table_t t, const float 
                   dp.device);
     p.blob = t->blob, p.enc_bytes = (t->enc_bytes + 15u) & ~15u;
     CAI_CHECK_ARG(p.enc_bytes <= static_cast<uint32_t>(t->blob_bytes), "ar decode: table blob too small");
+    p.stage_bytes = p.enc_bytes;
   } else {
     CAI_CHECK_ARG(y && sym && idx, "ar encode: null pointer");
   }
@@ -414,6 +468,15 @@ static int ar_run(const cai_ar_desc *d, bool decode, cai_table_t t, const float 
   CAI_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "ar scan: images per cluster must be 1, 2, 4 or 8");
   CAI_CHECK_ARG(G <= R, "ar scan: images per cluster (%d) cannot exceed the cluster size (%d)", G, R);
   while (G > 1 && ar_smem_bytes(p, G, decode) > static_cast<size_t>(dp.max_smem_optin) - 1024) G /= 2;
+  if (decode && (t->blob_bytes & 15) == 0 && (d->flags & 1)) {
+    // On request, stage the decode LUT too when the whole blob fits beside the G activation sets.  Off by default:
+    // measured on B200 the 187 KB blob leaves ~50 KB of L1 and the weight streaming of the four layers (the bound of
+    // the pixel step) slows down by more than the LUT saves on the chain (B = 16, R = 4: decode scan 125 -> 174 ms).
+    ArKernelParams q = p;
+    q.stage_bytes = static_cast<uint32_t>(t->blob_bytes);
+    if (q.stage_bytes > p.enc_bytes && ar_smem_bytes(q, G, true) <= static_cast<size_t>(dp.max_smem_optin) - 1024)
+      p.stage_bytes = q.stage_bytes;
+  }
   const size_t smem = ar_smem_bytes(p, G, decode);
 #define CAI_AR_LAUNCH(GG)                                                   \
   case GG:                                                                  \

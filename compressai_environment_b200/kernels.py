@@ -171,7 +171,8 @@ class ArWeights:
         self.widths = [int(cw.shape[0]) for cw, _ in convs]
         self.in_width = int(convs[0][0].shape[1])
 
-    def desc(self, params: torch.Tensor, scale_table: torch.Tensor, scale_bound: float, cluster: int = 0, group: int = 0):
+    def desc(self, params: torch.Tensor, scale_table: torch.Tensor, scale_bound: float, cluster: int = 0, group: int = 0,
+             flags: int = 0):
         """``params``: fp32 [B, H, W, P] contiguous (NHWC).  Returns (ArDesc, keep-alive tuple)."""
         from ._lib import ArDesc
 
@@ -186,7 +187,7 @@ class ArWeights:
         d.scale_bound, d.slope = float(scale_bound), self.slope
         d.T, d.B, d.H, d.W, d.M, d.P, d.n_ctx = int(tab.numel()), B, H, W, self.M, P, self.n_ctx
         d.n1, d.n2, d.n3 = self.widths
-        d.ksize, d.cluster, d.group = self.ksize, int(cluster), int(group)
+        d.ksize, d.cluster, d.group, d.flags = self.ksize, int(cluster), int(group), int(flags)
         return d, (tab, params)
 
 
@@ -212,7 +213,7 @@ def ar_encode(weights: ArWeights, y: torch.Tensor, params: torch.Tensor, scale_t
 
 
 def ar_decode(weights: ArWeights, table, words: torch.Tensor, word_begin: torch.Tensor, params: torch.Tensor, scale_table,
-              scale_bound: float, cluster: int = 0, group: int = 0, want_symbols: bool = False):
+              scale_bound: float, cluster: int = 0, group: int = 0, want_symbols: bool = False, use_lut: bool = False):
     """Decoder scan (reference ``_decompress_ar``, models/google.py:620-661): one rANS stream per image, M symbols per
     latent pixel in raster order.  ``table``: coder.CdfTable; ``words`` / ``word_begin``: the packed strings on the
     device (coder.strings_to_device).  Returns (padded y_hat [B, H+2p, W+2p, M], status int32 [B], symbols or None)."""
@@ -226,7 +227,7 @@ def ar_decode(weights: ArWeights, table, words: torch.Tensor, word_begin: torch.
     y_hat = torch.zeros((B, H + 2 * p, W + 2 * p, M), dtype=torch.float32, device=dev)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     sym = torch.empty((B, H * W * M), dtype=torch.int32, device=dev) if want_symbols else None
-    d, keep = weights.desc(params, scale_table, scale_bound, cluster, group)
+    d, keep = weights.desc(params, scale_table, scale_bound, cluster, group, 1 if use_lut else 0)
     with torch.cuda.device(dev):
         check(lib().cai_ar_decode(ctypes.byref(d), table.handle, ptr(words), ptr(word_begin), ptr(y_hat), ptr(sym),
                                   ptr(status), current_stream()), "cai_ar_decode")

@@ -350,6 +350,7 @@ typedef struct cai_ar_desc {
   float scale_bound, slope;
   int32_t T, B, H, W, M, P, n_ctx, n1, n2, n3, ksize;
   int32_t cluster, group;
+  int32_t flags;             /* bit 0: decoder also stages the decode LUT (slower on B200: it costs L1) */
 } cai_ar_desc;
 
 int cai_ar_encode(const cai_ar_desc *d, const float *y, float *y_hat, int32_t *sym, int32_t *idx, cai_stream_t stream);

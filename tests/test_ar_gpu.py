@@ -153,6 +153,10 @@ def _scan_parity(net, g, sd, orc):
                                             group, want_symbols=True)
         assert int(status.abs().max()) == 0
         assert torch.equal(s3, base[0]) and torch.equal(yh3, base[2]), (cluster, group)
+    # the decoder with the staged decode LUT (optional path) gives the same symbols
+    yh4, status, s4 = kernels.ar_decode(w, gc._table(), words, wb, p_n, gc.scale_table, gc._bound_scale(), want_symbols=True,
+                                        use_lut=True)
+    assert int(status.abs().max()) == 0 and torch.equal(s4, base[0]) and torch.equal(yh4, base[2])
     with torch.no_grad():
         x_hat = net.g_s(base[2][:, p:-p, p:-p, :].permute(0, 3, 1, 2), clamp=(0.0, 1.0), nchw_out=True)
     assert np.abs(x_hat.cpu().numpy() - g["x_hat"]).max() <= _xhat_tol(g)
