@@ -25,10 +25,6 @@
 // after the barrier that follows the owner's store.
 #include <cooperative_groups.h>
 
-#include <mutex>
-#include <set>
-#include <utility>
-
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
