@@ -231,3 +231,87 @@ def test_jarhp_training_step_backward():
     missing = [n for n, p in net.named_parameters() if p.grad is None and not n.endswith("quantiles")]
     assert not missing, missing
     assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,M,H,W,ksize,cluster,group", [(3, 20, 5, 7, 5, 2, 2), (1, 8, 1, 1, 3, 1, 1), (5, 36, 3, 9, 5, 4, 4),
+                                                         (2, 12, 6, 4, 7, 8, 1)])
+def test_scan_kernel_ragged_shapes(golden, B, M, H, W, ksize, cluster, group):
+    """The scan kernels on shapes the models do not produce: batch not a multiple of the images per cluster (phantom
+    image slots), channel counts that are multiples of 4 only, single-pixel grids, 3x3 / 7x7 context kernels, layer
+    widths that need K padding.  Encoder vs a plain-torch restatement of the reference loop (google.py:535-577) on the
+    GPU (rounding-boundary flips tolerated), and decoder(encoder strings) == encoder exactly."""
+    from compressai_environment_b200 import coder, kernels
+
+    g = golden("cdf")
+    dev = torch.device(DEV)
+    table = coder.CdfTable(*(torch.from_numpy(g[k]).to(dev) for k in ("gc_cdf", "gc_len", "gc_off")))
+    scale_table = torch.from_numpy(g["gc_scale_table"]).to(dev)
+    gen = torch.Generator().manual_seed(B * 1000 + M)
+    n_ctx, P = 2 * M, 2 * M
+    n1, n2, n3 = M * 10 // 3, M * 8 // 3, 2 * M
+    wc = torch.randn(n_ctx, M, ksize, ksize, generator=gen) * (0.4 / (ksize * M ** 0.5))
+    mask = torch.ones_like(wc)
+    mask[:, :, ksize // 2, ksize // 2:] = 0
+    mask[:, :, ksize // 2 + 1:] = 0
+    bc = torch.randn(n_ctx, generator=gen) * 0.1
+    dims = [(P + n_ctx, n1), (n1, n2), (n2, n3)]
+    convs = [(torch.randn(o, i, 1, 1, generator=gen) * (1.5 / i ** 0.5), torch.randn(o, generator=gen) * 0.3) for i, o in dims]
+    y = (torch.randn(B, M, H, W, generator=gen) * 6).to(dev)
+    params = torch.randn(B, P, H, W, generator=gen).to(dev)
+    wts = kernels.ArWeights((wc * mask).to(dev), bc.to(dev), [(a.to(dev), b.to(dev)) for a, b in convs])
+    yn, pn = y.permute(0, 2, 3, 1).contiguous(), params.permute(0, 2, 3, 1).contiguous()
+    sym, idx, yh = kernels.ar_encode(wts, yn, pn, scale_table, 0.11, cluster, group)
+    # plain-torch restatement of the loop
+    pad = ksize // 2
+    w2 = (wc * mask).flatten(1).to(dev)
+    E = [(a.flatten(1).to(dev), b.to(dev)) for a, b in convs]
+    ref_h = torch.nn.functional.pad(y.clone(), (pad, pad, pad, pad))
+    rs = torch.zeros_like(sym)
+    ri = torch.zeros_like(idx)
+    for h in range(H):
+        for w in range(W):
+            ctx = ref_h[:, :, h:h + ksize, w:w + ksize].reshape(B, -1) @ w2.t() + bc.to(dev)
+            v = torch.cat((params[:, :, h, w], ctx), 1)
+            v = torch.nn.functional.leaky_relu(v @ E[0][0].t() + E[0][1])
+            v = torch.nn.functional.leaky_relu(v @ E[1][0].t() + E[1][1])
+            v = v @ E[2][0].t() + E[2][1]
+            sc, mu = v[:, :M].clamp(min=0.11), v[:, M:]
+            k = (scale_table.numel() - 1) - (sc[:, :, None] <= scale_table[None, None, :-1]).sum(-1)
+            q = torch.round(y[:, :, h, w] - mu)
+            ref_h[:, :, h + pad, w + pad] = q + mu
+            o = (h * W + w) * M
+            rs[:, o:o + M], ri[:, o:o + M] = q.int(), k.int()
+    flips = float((rs != sym).float().mean()) + float((ri != idx).float().mean())
+    assert flips <= 0.02, flips
+    if flips == 0.0:
+        assert float((yh.permute(0, 3, 1, 2) - ref_h).abs().max()) <= 1e-3 * float(ref_h.abs().max())
+    # coder + decoder scan: exact round trip
+    enc = coder.encode(table, sym, idx)
+    assert int(enc.status.abs().max()) == 0
+    strings = [bytes(s) for s in enc.to_bytes()]
+    words, wb, keep = coder.strings_to_device(strings, dev)
+    for cl, gr in ((cluster, group), (0, 0), (1, 1)):
+        yh2, status, s2 = kernels.ar_decode(wts, table, words, wb, pn, scale_table, 0.11, cl, gr, want_symbols=True)
+        assert int(status.abs().max()) == 0
+        assert torch.equal(s2, sym) and torch.equal(yh2, yh), (cl, gr)
+
+
+@pytest.mark.gpu
+def test_scan_kernel_rejects_bad_arguments(golden):
+    from compressai_environment_b200 import kernels
+    from compressai_environment_b200._lib import CaiError
+
+    dev = torch.device(DEV)
+    M = 6  # not a multiple of 4
+    wts = kernels.ArWeights(torch.zeros(2 * M, M, 5, 5, device=dev), torch.zeros(2 * M, device=dev),
+                            [(torch.zeros(20, 4 * M, 1, 1, device=dev), torch.zeros(20, device=dev)),
+                             (torch.zeros(16, 20, 1, 1, device=dev), torch.zeros(16, device=dev)),
+                             (torch.zeros(2 * M, 16, 1, 1, device=dev), torch.zeros(2 * M, device=dev))])
+    y = torch.zeros(1, 2, 2, M, device=dev)
+    p = torch.zeros(1, 2, 2, 2 * M, device=dev)
+    tab = torch.from_numpy(golden("cdf")["gc_scale_table"]).to(dev)
+    with pytest.raises(CaiError):
+        kernels.ar_encode(wts, y, p, tab, 0.11)
+    with pytest.raises(ValueError):  # params channels do not match entropy_parameters' input width
+        kernels.ar_encode(wts, y, torch.zeros(1, 2, 2, M, device=dev), tab, 0.11)
