@@ -1043,11 +1043,13 @@ static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
   // A string is a serial chain: its warp issues ~0.2 instructions per cycle, so several strings share an SM
   // sub-partition without slowing each other much.  Few, fat CTAs (>= 8 warps) keep the coder on a handful of
   // SMs -- each CTA pins a copy of the table in shared memory -- and leave the rest of the chip to the
-  // transform kernels running concurrently on other streams.
+  // transform kernels running concurrently on other streams.  Measured on the headline step (32 strings per launch):
+  // 16 warps per CTA (2 SMs per launch) lengthen the chains by 15-20 % (decode 73 -> 85 ms per launch) but halve the
+  // coder's SM-time, and the step gains 1.3 % (104.5 -> 103.1 ms); 32 warps per CTA lose (138 ms).
   int w = (B + dp.sm_count / 4 - 1) / (dp.sm_count / 4 > 0 ? dp.sm_count / 4 : 1);
   const int kw = knobs().coder_warps;
   if (kw >= 1 && kw <= kMaxWarpsPerCta) w = w > kw ? w : kw;
-  else if (w < 8) w = 8;
+  else if (w < 16) w = 16;
   if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
   if (w > B) w = B < 1 ? 1 : B;
   int g = (B + w - 1) / w;
