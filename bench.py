@@ -1031,7 +1031,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true", help="skip the as-is / trained-rate / C1 / C4 variants")
     ap.add_argument("--gain-y", type=float, default=GAIN_Y, help="scale of the last g_a layer (stream rate, see GAIN_Y)")
     ap.add_argument("--gain-s", type=float, default=GAIN_S, help="scale of the last h_s layer")
-    ap.add_argument("--inflight", type=int, default=3, help="steps in flight (user streams) in the device-timed loop")
+    ap.add_argument("--inflight", type=int, default=4, help="steps in flight (user streams) in the device-timed loop")
     ap.add_argument("--e2e-inflight", type=int, default=5, help="requests in flight (host threads) in the e2e loop")
     ap.add_argument("--pin-cores", default="auto", choices=["auto", "on", "off"],
                     help="bind each rank to its own CPUs next to its GPU (auto: only when there are several ranks)")
