@@ -665,17 +665,35 @@ __global__ void __launch_bounds__(256)
 im2col_k5s2_c3_kernel(const float *__restrict__ x, int layout, int H, int W, int Ho, int Wo, int Kpad,
                       __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
   __shared__ float s_patch[3][kI2cPR][kI2cPitch];
+  __shared__ int s_koff[80];  // k -> offset of tap (ky, kx), channel c inside the patch; -1 for the K padding
+  if (threadIdx.x < 80) {
+    const int k = threadIdx.x, t = k / 3, c = k - 3 * t, ky = t / 5, kx = t - 5 * ky;
+    s_koff[k] = k < 75 ? (c * kI2cPR + ky) * kI2cPitch + kx : -1;
+  }
   const int n = blockIdx.z, oy0 = blockIdx.y * kI2cTY, ox0 = blockIdx.x * kI2cTX;
   const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
-  for (int u = threadIdx.x; u < 3 * kI2cPR * kI2cPC; u += 256) {
-    const int c = u / (kI2cPR * kI2cPC), rem = u - c * (kI2cPR * kI2cPC);
-    const int r = rem / kI2cPC, col = rem - r * kI2cPC;
-    const int iy = iy0 + r, ix = ix0 + col;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v = (layout == CAI_LAYOUT_NHWC) ? __ldg(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * 3 + c)
-                                      : __ldg(x + ((static_cast<int64_t>(n) * 3 + c) * H + iy) * W + ix);
-    s_patch[c][r][col] = v;
+  constexpr int kPatch = 3 * kI2cPR * kI2cPC;
+  for (int u0 = threadIdx.x; u0 < kPatch; u0 += 6 * 256) {  // six loads in flight per thread
+    float v[6];
+    int cc[6], rr[6], col[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const int u = u0 + e * 256;
+      v[e] = 0.f;
+      cc[e] = -1;
+      if (u < kPatch) {
+        const int c = u / (kI2cPR * kI2cPC), rem = u - c * (kI2cPR * kI2cPC);
+        const int r = rem / kI2cPC, cl = rem - r * kI2cPC;
+        const int iy = iy0 + r, ix = ix0 + cl;
+        cc[e] = c, rr[e] = r, col[e] = cl;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v[e] = (layout == CAI_LAYOUT_NHWC) ? __ldg(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * 3 + c)
+                                             : __ldg(x + ((static_cast<int64_t>(n) * 3 + c) * H + iy) * W + ix);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+      if (cc[e] >= 0) s_patch[cc[e]][rr[e]][col[e]] = v[e];
   }
   __syncthreads();
   const int groups = Kpad >> 3;
@@ -685,16 +703,11 @@ im2col_k5s2_c3_kernel(const float *__restrict__ x, int layout, int H, int W, int
     const int oy = oy0 + py, ox = ox0 + px;
     if (oy >= Ho || ox >= Wo) continue;
     float v[8];
+    const float *base = &s_patch[0][0][0] + (2 * py) * kI2cPitch + 2 * px;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float val = 0.f;
-      if (k < 75) {
-        const int t = k / 3, c = k - 3 * t;
-        const int ky = t / 5, kx = t - 5 * ky;
-        val = s_patch[c][2 * py + ky][2 * px + kx];
-      }
-      v[j] = val;
+      const int off = (g * 8 + j < 80) ? s_koff[g * 8 + j] : -1;
+      v[j] = off >= 0 ? base[off] : 0.f;
     }
     const Pack8 pk = split8(v);
     const int64_t o = ((static_cast<int64_t>(n) * Ho + oy) * Wo + ox) * Kpad + g * 8;
@@ -718,15 +731,33 @@ col2im_k5s2_c3_kernel(const float *__restrict__ cols, const float *__restrict__ 
   extern __shared__ float s_cols[];
   const int n = blockIdx.z, oy0 = blockIdx.y * kC2iTY, ox0 = blockIdx.x * kC2iTX;
   const int iy0 = oy0 / 2 - 1, ix0 = ox0 / 2 - 1;
-  for (int u = threadIdx.x; u < kC2iIY * kC2iIX * 19; u += 256) {
-    const int pix = u / 19, q = u - pix * 19;
-    const int ly = pix / kC2iIX, lx = pix - ly * kC2iIX;
-    const int iy = iy0 + ly, ix = ix0 + lx;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v = __ldcs(reinterpret_cast<const float4 *>(cols + ((static_cast<int64_t>(n) * H + iy) * W + ix) * Npad) + q);
-    float *d = s_cols + pix * kC2iPitch + q * 4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  // staging: kC2iIY * kC2iIX * 19 float4 units, four loads in flight per thread before the first store (the loop as a
+  // load -> store chain left one 16-byte request per thread outstanding: 2.5 TB/s)
+  constexpr int kUnits = kC2iIY * kC2iIX * 19;
+  for (int u0 = threadIdx.x; u0 < kUnits; u0 += 4 * 256) {
+    float4 v[4];
+    int dsto[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int u = u0 + e * 256;
+      v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dsto[e] = -1;
+      if (u < kUnits) {
+        const int pix = u / 19, q = u - pix * 19;
+        const int ly = pix / kC2iIX, lx = pix - ly * kC2iIX;
+        const int iy = iy0 + ly, ix = ix0 + lx;
+        dsto[e] = pix * kC2iPitch + q * 4;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v[e] = __ldcs(reinterpret_cast<const float4 *>(cols + ((static_cast<int64_t>(n) * H + iy) * W + ix) * Npad) + q);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (dsto[e] >= 0) {
+        float *d = s_cols + dsto[e];
+        d[0] = v[e].x; d[1] = v[e].y; d[2] = v[e].z; d[3] = v[e].w;
+      }
+    }
   }
   __syncthreads();
   const int ty = threadIdx.x >> 5, jx = threadIdx.x & 31;
