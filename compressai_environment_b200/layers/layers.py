@@ -38,20 +38,21 @@ def _conv_act(conv: Conv2d, act, x: Tensor) -> Tensor:
 
 class MaskedConv2d(Conv2d):
     """Masked convolution for autoregressive context models: type "A" hides the current pixel and everything after it
-    in raster order, type "B" keeps the current pixel.  The mask is a buffer applied to ``weight.data`` on every
-    forward, as in the reference."""
+    in raster order, type "B" keeps the current pixel.  The mask is a buffer (``state_dict`` key ``mask``) multiplied
+    into ``weight.data`` on every forward, as in the reference."""
 
     def __init__(self, in_channels, out_channels, kernel_size=5, stride=1, padding=None, mask_type: str = "A"):
-        super().__init__(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
-        if mask_type not in ("A", "B"):
+        if mask_type != "A" and mask_type != "B":
             raise ValueError(f'Invalid "mask_type" value "{mask_type}"')
-        self.register_buffer("mask", torch.ones_like(self.weight.data))
-        _, _, h, w = self.mask.size()
-        self.mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
-        self.mask[:, :, h // 2 + 1:] = 0
+        super().__init__(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+        k = self.kernel_size
+        causal = torch.zeros(k * k)
+        causal[: (k // 2) * k + k // 2 + (1 if mask_type == "B" else 0)] = 1  # raster-order prefix of the window
+        self.register_buffer("mask", causal.view(1, 1, k, k).expand_as(self.weight).clone())
 
     def forward(self, x: Tensor) -> Tensor:
-        self.weight.data *= self.mask
+        with torch.no_grad():
+            self.weight.mul_(self.mask)  # bumps the version counter: the packed-weight cache sees the change
         return super().forward(x)
 
 
@@ -68,86 +69,86 @@ def conv1x1(in_ch: int, out_ch: int, stride: int = 1) -> nn.Module:
     return Conv2d(in_ch, out_ch, kernel_size=1, stride=stride, padding=0)
 
 
+def _conv_gdn(conv: Conv2d, gdn: GDN, x: Tensor) -> Tensor:
+    """conv followed by GDN / IGDN: one launch in inference (second in-kernel GEMM)."""
+    if _inference(x, conv, gdn):
+        return run_stack([conv, gdn], x)
+    return gdn(conv(x))
+
+
 class ResidualBlockWithStride(nn.Module):
+    """conv3x3(stride) - LeakyReLU - conv3x3 - GDN, plus a 1x1 strided skip (reference layers.py:101-135)."""
+
     def __init__(self, in_ch: int, out_ch: int, stride: int = 2):
         super().__init__()
-        self.conv1 = conv3x3(in_ch, out_ch, stride=stride)
-        self.leaky_relu = nn.LeakyReLU(inplace=True)
-        self.conv2 = conv3x3(out_ch, out_ch)
-        self.gdn = GDN(out_ch)
-        self.skip = conv1x1(in_ch, out_ch, stride=stride) if (stride != 1 or in_ch != out_ch) else None
+        needs_skip = stride != 1 or in_ch != out_ch
+        self.conv1, self.leaky_relu = conv3x3(in_ch, out_ch, stride=stride), nn.LeakyReLU(inplace=True)
+        self.conv2, self.gdn = conv3x3(out_ch, out_ch), GDN(out_ch)
+        self.skip = conv1x1(in_ch, out_ch, stride=stride) if needs_skip else None
 
     def forward(self, x: Tensor) -> Tensor:
-        out = _conv_act(self.conv1, self.leaky_relu, x)
-        if _inference(out, self.conv2, self.gdn):
-            out = run_stack([self.conv2, self.gdn], out)  # conv + GDN in one launch
-        else:
-            out = self.gdn(self.conv2(out))
-        identity = self.skip(x) if self.skip is not None else x
-        return out + identity
+        main = _conv_gdn(self.conv2, self.gdn, _conv_act(self.conv1, self.leaky_relu, x))
+        return main + (x if self.skip is None else self.skip(x))
 
 
 class ResidualBlockUpsample(nn.Module):
+    """subpel conv - LeakyReLU - conv3x3 - IGDN, plus a sub-pixel skip (reference layers.py:138-168)."""
+
     def __init__(self, in_ch: int, out_ch: int, upsample: int = 2):
         super().__init__()
-        self.subpel_conv = subpel_conv3x3(in_ch, out_ch, upsample)
-        self.leaky_relu = nn.LeakyReLU(inplace=True)
-        self.conv = conv3x3(out_ch, out_ch)
-        self.igdn = GDN(out_ch, inverse=True)
+        self.subpel_conv, self.leaky_relu = subpel_conv3x3(in_ch, out_ch, upsample), nn.LeakyReLU(inplace=True)
+        self.conv, self.igdn = conv3x3(out_ch, out_ch), GDN(out_ch, inverse=True)
         self.upsample = subpel_conv3x3(in_ch, out_ch, upsample)
 
     def forward(self, x: Tensor) -> Tensor:
+        conv, shuffle = self.subpel_conv
         # LeakyReLU commutes with the pixel shuffle (a permutation): fold it into the conv launch
-        out = self.subpel_conv[1](_conv_act(self.subpel_conv[0], self.leaky_relu, x))
-        if _inference(out, self.conv, self.igdn):
-            out = run_stack([self.conv, self.igdn], out)
-        else:
-            out = self.igdn(self.conv(out))
-        return out + self.upsample(x)
+        main = _conv_gdn(self.conv, self.igdn, shuffle(_conv_act(conv, self.leaky_relu, x)))
+        return main + self.upsample(x)
 
 
 class ResidualBlock(nn.Module):
+    """Two conv3x3 + LeakyReLU with an identity (or 1x1) skip (reference layers.py:171-203)."""
+
     def __init__(self, in_ch: int, out_ch: int):
         super().__init__()
-        self.conv1 = conv3x3(in_ch, out_ch)
-        self.leaky_relu = nn.LeakyReLU(inplace=True)
+        self.conv1, self.leaky_relu = conv3x3(in_ch, out_ch), nn.LeakyReLU(inplace=True)
         self.conv2 = conv3x3(out_ch, out_ch)
-        self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
+        self.skip = None if in_ch == out_ch else conv1x1(in_ch, out_ch)
 
     def forward(self, x: Tensor) -> Tensor:
-        out = _conv_act(self.conv1, self.leaky_relu, x)
-        out = _conv_act(self.conv2, self.leaky_relu, out)
-        identity = self.skip(x) if self.skip is not None else x
-        return out + identity
+        main = _conv_act(self.conv2, self.leaky_relu, _conv_act(self.conv1, self.leaky_relu, x))
+        return main + (x if self.skip is None else self.skip(x))
 
 
-class AttentionBlock(nn.Module):
-    """Simplified self-attention block of Cheng et al. 2020: out = a(x) * sigmoid(b(x)) + x."""
+class _ResidualUnit(nn.Module):
+    """1x1 - ReLU - 3x3 - ReLU - 1x1 bottleneck with an identity skip (the unit of ``AttentionBlock``)."""
 
     def __init__(self, N: int):
         super().__init__()
-
-        class ResidualUnit(nn.Module):
-            def __init__(self):
-                super().__init__()
-                self.conv = nn.Sequential(conv1x1(N, N // 2), nn.ReLU(inplace=True), conv3x3(N // 2, N // 2),
-                                          nn.ReLU(inplace=True), conv1x1(N // 2, N))
-                self.relu = nn.ReLU(inplace=True)
-
-            def forward(self, x: Tensor) -> Tensor:
-                if _inference(x, self.conv):
-                    out = run_stack(list(self.conv), x)  # three launches, activations stay in split planes
-                else:
-                    out = self.conv(x)
-                return self.relu(out + x)
-
-        self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
-        self.conv_b = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit(), conv1x1(N, N))
+        half = N // 2
+        self.conv = nn.Sequential(conv1x1(N, half), nn.ReLU(inplace=True), conv3x3(half, half), nn.ReLU(inplace=True),
+                                  conv1x1(half, N))
+        self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x: Tensor) -> Tensor:
-        a = self.conv_a(x)
-        b = self.conv_b(x)
-        return a * torch.sigmoid(b) + x
+        # inference: three launches, activations stay in split planes between them
+        y = run_stack(list(self.conv), x) if _inference(x, self.conv) else self.conv(x)
+        return self.relu(y + x)
+
+
+class AttentionBlock(nn.Module):
+    """Simplified self-attention block of Cheng et al. 2020: out = a(x) * sigmoid(b(x)) + x (reference layers.py:206-244)."""
+
+    def __init__(self, N: int):
+        super().__init__()
+        self.conv_a = nn.Sequential(*(_ResidualUnit(N) for _ in range(3)))
+        self.conv_b = nn.Sequential(*(_ResidualUnit(N) for _ in range(3)), conv1x1(N, N))
+
+    def forward(self, x: Tensor) -> Tensor:
+        gate = torch.sigmoid(self.conv_b(x))
+        return self.conv_a(x) * gate + x
+
 
 _QRELU_ALPHA = 0.9943258522851727
 
