@@ -1050,7 +1050,13 @@ static int plan_grid(const DeviceProps &dp, int32_t B, int *warps, int *grid) {
   const int kw = knobs().coder_warps;
   if (kw >= 1 && kw <= kMaxWarpsPerCta) w = w > kw ? w : kw;
   else if (w < 16) w = 16;
-  if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+  if (w > kMaxWarpsPerCta) {
+    // thousands of strings (C3): the kernels are issue-bound (ncu r02: SM throughput 73-77 %), so every SM must carry
+    // its share -- 4096 strings as 128 CTAs x 32 warps left 20 of the 148 SMs idle; 147 CTAs x 28 warps use them all
+    w = (B + dp.sm_count - 1) / dp.sm_count;
+    if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+    if (w < 16) w = 16;
+  }
   if (w > B) w = B < 1 ? 1 : B;
   int g = (B + w - 1) / w;
   if (g > dp.sm_count) g = dp.sm_count;  // persistent: each warp strides over strings
