@@ -935,6 +935,9 @@ int cai_conv_gemm(const cai_conv_desc *d, cai_stream_t stream_) {
   // Multi-tap layers re-read each activation line from L1 for the later taps of a group: a shallower ring leaves
   // more of the unified L1/shared memory to the cache, which is worth more than the third stage (measured on the
   // 128->128 k5 s2 layer: 2.19 ms with 3 stages, 2.08 ms with 2).
+  // (Round 2: a per-layer rule that kept the third stage on stride-1 inputs and small grids made the layers 1.5 %
+  // faster alone -- 9.10 -> 8.97 ms per micro-batch -- and the overlapped step 3 % SLOWER, 104.4 vs 100.3-101.8 ms: the
+  // bigger CTAs co-reside worse with the kernels of the other streams.  Two stages stay.)
   if (d->ntaps > 1 && stages > 2) stages = 2;
   if (stages < 2) stages = static_cast<int>((static_cast<size_t>(dp.max_smem_optin) - 2048) / stage_bytes) >= 2 ? 2 : stages;
   const Knobs &kn = knobs();
