@@ -20,7 +20,9 @@ One step = compress + decompress of the whole batch.  Prints ONE JSON line on ra
              FLOPs / CUDA-event time; roofline_coder / roofline_index: the rANS decode and the fused index kernel
   rans_c3  : the raw coder on BASELINE configs[2] (2^28 symbols per GPU, 4096 strings), every rank, beside the
              reference's C++ coder timed on the box's host cores (1 core, and all cores through a process pool)
-  configs  : C1 (factorized q1, one image) and C4 (mbt2018-mean q8, one 3840x2176 frame) through the public API
+  e2e_u8   : the same public-API loop with uint8 host buffers (converted on the device; a quarter of the PCIe bytes)
+  configs  : C1 (factorized q1, one image), C4 (mbt2018-mean q8, one 3840x2176 frame) and the autoregressive mbt2018 q3
+             (16 images; csrc/ar.cu scan kernel) through the public API
   cpu_baseline : the UNMODIFIED reference (oracle/_ref) on the host cores, bounded sample of the same workload
 
 --impl reference times the reference's own CPU implementation (model.compress/decompress, torch CPU +
